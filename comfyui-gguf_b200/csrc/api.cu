@@ -1,0 +1,188 @@
+// api.cu -- the extern "C" boundary declared in include/ggufb200.h.
+// Argument validation lives here; kernels live in dequant.cu / rows.cu / gemv.cu / gemm.cu.
+#include "blocks.cuh"
+
+namespace ggufb200 {
+extern int g_dequant_ctas_per_sm;
+int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st);
+int unpack_dispatch(int type, const void *packed, long long n_blocks, int16_t *q, int16_t *sc, int16_t *mn, cudaStream_t st);
+int rows_dispatch(int type, const void *packed, long long n_table_rows, long long K, const long long *rows, long long n_rows,
+                  void *out, int out_dtype, int math_dtype, cudaStream_t st);
+int gemv_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
+                  int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
+                        int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
+                        int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm_fused_supported(int type);
+int gemv_max_m();
+}  // namespace ggufb200
+
+using namespace ggufb200;
+
+static bool type_geom(int t, int *bs, int *ts)
+{
+    int b = 0, s = 0;
+    switch (t) {
+    case T_Q4_0: b = 32; s = 18; break;
+    case T_Q4_1: b = 32; s = 20; break;
+    case T_Q5_0: b = 32; s = 22; break;
+    case T_Q5_1: b = 32; s = 24; break;
+    case T_Q8_0: b = 32; s = 34; break;
+    case T_Q2_K: b = 256; s = 84; break;
+    case T_Q3_K: b = 256; s = 110; break;
+    case T_Q4_K: b = 256; s = 144; break;
+    case T_Q5_K: b = 256; s = 176; break;
+    case T_Q6_K: b = 256; s = 210; break;
+    case T_IQ4_NL: b = 32; s = 18; break;
+    case T_IQ4_XS: b = 256; s = 136; break;
+    case T_BF16: b = 1; s = 2; break;
+    default: return false;
+    }
+    if (bs) *bs = b;
+    if (ts) *ts = s;
+    return true;
+}
+
+static bool dtype_ok(int d) { return d >= 0 && d <= 2; }
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" {
+
+int ggufb200_version(void) { return GGUFB200_VERSION; }
+
+const char *ggufb200_strerror(int rc)
+{
+    switch (rc) {
+    case GGUFB200_OK: return "ok";
+    case GGUFB200_E_TYPE: return "unsupported ggml quantization type (no CPU fallback is provided)";
+    case GGUFB200_E_DTYPE: return "dtype code must be 0 (float16), 1 (bfloat16) or 2 (float32)";
+    case GGUFB200_E_ALIGN: return "output / activation pointers must be 16-byte aligned";
+    case GGUFB200_E_SHAPE: return "bad shape: sizes must be non-negative, K a multiple of the block size, ld >= row length";
+    case GGUFB200_E_NULL: return "required pointer is NULL";
+    case GGUFB200_E_CUDA: return "CUDA launch failed";
+    case GGUFB200_E_WORKSPACE: return "workspace too small (see ggufb200_linear_workspace)";
+    case GGUFB200_E_UNSUPPORTED: return "operation not implemented for this type / dtype combination";
+    case GGUFB200_E_DEVICE: return "current CUDA device is not sm_100 (B200)";
+    }
+    return "unknown error";
+}
+
+int ggufb200_type_info(int ggml_type, int *block_size, int *type_size)
+{
+    return type_geom(ggml_type, block_size, type_size) ? GGUFB200_OK : GGUFB200_E_TYPE;
+}
+
+int ggufb200_supported(int ggml_type, int op)
+{
+    if (!type_geom(ggml_type, nullptr, nullptr)) return 0;
+    switch (op) {
+    case GGUFB200_OP_DEQUANT: return 1;
+    case GGUFB200_OP_ROWS: return 1;
+    case GGUFB200_OP_LINEAR: return 1;
+    case GGUFB200_OP_LINEAR_MMA: return gemm_fused_supported(ggml_type) ? 1 : 0;
+    }
+    return 0;
+}
+
+int ggufb200_set_tuning(int key, int value)
+{
+    if (key == 0) {
+        g_dequant_ctas_per_sm = value;
+        return GGUFB200_OK;
+    }
+    return GGUFB200_E_UNSUPPORTED;
+}
+
+int ggufb200_dequant(int ggml_type, const void *packed, int64_t n_blocks, void *out, int out_dtype, int math_dtype, void *stream)
+{
+    if (!type_geom(ggml_type, nullptr, nullptr)) return GGUFB200_E_TYPE;
+    if (!dtype_ok(out_dtype) || !dtype_ok(math_dtype)) return GGUFB200_E_DTYPE;
+    if (n_blocks < 0) return GGUFB200_E_SHAPE;
+    if (n_blocks == 0) return GGUFB200_OK;
+    if (!packed || !out) return GGUFB200_E_NULL;
+    if (!aligned16(out)) return GGUFB200_E_ALIGN;
+    return dequant_dispatch(ggml_type, packed, n_blocks, out, out_dtype, math_dtype, (cudaStream_t)stream);
+}
+
+int ggufb200_unpack_int(int ggml_type, const void *packed, int64_t n_blocks, int16_t *q, int16_t *sc, int16_t *mn, void *stream)
+{
+    if (!type_geom(ggml_type, nullptr, nullptr) || ggml_type == T_BF16) return GGUFB200_E_TYPE;
+    if (n_blocks < 0) return GGUFB200_E_SHAPE;
+    if (n_blocks == 0) return GGUFB200_OK;
+    if (!packed) return GGUFB200_E_NULL;
+    return unpack_dispatch(ggml_type, packed, n_blocks, q, sc, mn, (cudaStream_t)stream);
+}
+
+int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_rows, int64_t K, const int64_t *rows, int64_t n_rows,
+                          void *out, int out_dtype, int math_dtype, void *stream)
+{
+    int bs, ts;
+    if (!type_geom(ggml_type, &bs, &ts)) return GGUFB200_E_TYPE;
+    if (!dtype_ok(out_dtype) || !dtype_ok(math_dtype)) return GGUFB200_E_DTYPE;
+    if (n_rows < 0 || n_table_rows < 0 || K <= 0 || K % bs != 0 || K % 8 != 0) return GGUFB200_E_SHAPE;
+    if (n_rows == 0) return GGUFB200_OK;
+    if (!packed || !rows || !out) return GGUFB200_E_NULL;
+    if (!aligned16(out)) return GGUFB200_E_ALIGN;
+    return rows_dispatch(ggml_type, packed, n_table_rows, K, (const long long *)rows, n_rows, out, out_dtype, math_dtype,
+                         (cudaStream_t)stream);
+}
+
+size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo)
+{
+    (void)M;
+    if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0) return 0;
+    if (algo == GGUFB200_ALGO_DEQUANT_MMA) return (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
+    return 0;
+}
+
+int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx, int act_dtype,
+                    int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace, size_t workspace_bytes,
+                    int algo, void *stream)
+{
+    int bs, ts;
+    if (!type_geom(ggml_type, &bs, &ts)) return GGUFB200_E_TYPE;
+    if (act_dtype != kF16 && act_dtype != kBF16) return GGUFB200_E_DTYPE;
+    if (!dtype_ok(math_dtype) || (bias && !dtype_ok(bias_dtype))) return GGUFB200_E_DTYPE;
+    if (M < 0 || N <= 0 || K <= 0 || K % bs != 0 || K % 8 != 0 || ldx < K || ldy < N) return GGUFB200_E_SHAPE;
+    if (M == 0) return GGUFB200_OK;
+    if (!W_packed || !X || !Y) return GGUFB200_E_NULL;
+    if (!aligned16(X) || !aligned16(Y) || (ldx % 8) != 0 || (ldy % 8) != 0) return GGUFB200_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    if (algo == GGUFB200_ALGO_AUTO) {
+        if (M <= gemv_max_m()) algo = GGUFB200_ALGO_GEMV;
+        else if (gemm_fused_supported(ggml_type)) algo = GGUFB200_ALGO_FUSED_MMA;
+        else algo = GGUFB200_ALGO_DEQUANT_MMA;
+    }
+    switch (algo) {
+    case GGUFB200_ALGO_GEMV:
+        return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case GGUFB200_ALGO_FUSED_MMA:
+        if (!gemm_fused_supported(ggml_type)) return GGUFB200_E_UNSUPPORTED;
+        return gemm_fused_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case GGUFB200_ALGO_DEQUANT_MMA: {
+        size_t need = (size_t)N * (size_t)K * 2;
+        if (!workspace || workspace_bytes < need) return GGUFB200_E_WORKSPACE;
+        if (!aligned16(workspace)) return GGUFB200_E_ALIGN;
+        int rc = dequant_dispatch(ggml_type, W_packed, N * (K / bs), workspace, act_dtype, math_dtype, st);
+        if (rc != GGUFB200_OK) return rc;
+        return gemm_dense_dispatch(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
+    }
+    }
+    return GGUFB200_E_UNSUPPORTED;
+}
+
+int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx, int act_dtype,
+                  const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream)
+{
+    if (act_dtype != kF16 && act_dtype != kBF16) return GGUFB200_E_DTYPE;
+    if (bias && !dtype_ok(bias_dtype)) return GGUFB200_E_DTYPE;
+    if (M < 0 || N <= 0 || K <= 0 || K % 8 != 0 || ldw < K || ldx < K || ldy < N) return GGUFB200_E_SHAPE;
+    if (M == 0) return GGUFB200_OK;
+    if (!W || !X || !Y) return GGUFB200_E_NULL;
+    if (!aligned16(W) || !aligned16(X) || !aligned16(Y) || (ldw % 8) || (ldx % 8) || (ldy % 8)) return GGUFB200_E_ALIGN;
+    return gemm_dense_dispatch(W, N, K, ldw, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// blocks.cuh -- per-format unpack of GGUF quantised blocks (device side).
+//
+// One struct per ggml type (the keys of the reference's dispatch table, dequant.py:287-301).
+// Every struct exposes the same interface so the standalone dequant kernel, the row-gather
+// kernel, the fused GEMV and the fused tcgen05 GEMM all share one unpack implementation:
+//
+//   BS, TS      block size (elements) and type size (bytes)          gguf-py GGML_QUANT_SIZES
+//   BIAS        q4() returns u = q + BIAS as unsigned bytes (q = integer entering the multiply)
+//   KIND        float step:  0  d*q            1  d*q + m
+//                            2  (d*sc)*q       3  (d*sc)*q - (dmin*mn)
+//   q4(blk,e0)  four consecutive elements e0..e0+3 (e0 % 4 == 0) as four biased bytes
+//   scales()    integer sub-block scale / min of the group containing e0 (constant over
+//               any aligned run of 8 elements for every format)
+//   d_bits / d2_bits   raw fp16 header fields
+//
+// `blk` points at the first byte of the block; A_BLK = its compile-time known alignment
+// (gcd(TS,16) when the tile base is 16-byte aligned).  Everything here is integer work and
+// is bit-exact against oracle/gguf_oracle.c::unpack_elem and the reference.
+#pragma once
+#include "common.cuh"
+
+namespace ggufb200 {
+
+enum : int {
+    T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12,
+    T_Q5_K = 13, T_Q6_K = 14, T_IQ4_NL = 20, T_IQ4_XS = 23, T_BF16 = 30
+};
+
+// spread the low four bits of t over the low bit of four bytes (bit i -> byte i)
+__device__ __forceinline__ uint32_t spread4(uint32_t t) { return ((t & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+// dequant.py:241 value table, stored biased by +127 so it fits unsigned bytes
+__device__ __forceinline__ uint32_t iq4_lookup4(uint32_t idx4)
+{
+    // entries 0..15 of (KVALUES + 127):  0 23 44 62 | 78 92 105 117 | 128 140 152 165 | 180 196 216 240
+    const uint32_t t0 = 0x3E2C1700u, t1 = 0x75695C4Eu, t2 = 0xA5988C80u, t3 = 0xF0D8C4B4u;
+    // prmt can index 8 bytes; pick from the low or the high half of the table by bit 3 of each index
+    uint32_t sel = (idx4 & 0x07070707u);
+    sel = (sel | (sel >> 4)) & 0x00FF00FFu;          // pack nibbles: byte0|byte1 -> low byte, byte2|byte3 -> byte 2
+    sel = (sel | (sel >> 8)) & 0x0000FFFFu;          // four selector nibbles in the low 16 bits
+    uint32_t lo = prmt(t0, t1, sel);
+    uint32_t hi = prmt(t2, t3, sel);
+    uint32_t m = ((idx4 >> 3) & 0x01010101u) * 0xFFu;  // 0xFF per byte whose index >= 8
+    return (lo & ~m) | (hi & m);
+}
+
+template <int QT> struct Block;
+
+// ---------------------------------------------------------------- legacy 32-element blocks
+template <> struct Block<T_Q4_0> {  // dequant.py:115-123   [d f16][qs 16]
+    static constexpr int BS = 32, TS = 18, BIAS = 8, KIND = 0, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        return (ld32<2>(b + 2 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+template <> struct Block<T_Q4_1> {  // dequant.py:103-113   [d][m][qs 16]
+    static constexpr int BS = 32, TS = 20, BIAS = 0, KIND = 1, A_BLK = 4;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<4>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        return (ld32<4>(b + 4 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+template <> struct Block<T_Q5_0> {  // dequant.py:87-101   [d][qh u32][qs 16]
+    static constexpr int BS = 32, TS = 22, BIAS = 16, KIND = 0, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        uint32_t qh = ld32<2>(b + 2);
+        uint32_t lo = (ld32<2>(b + 6 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
+        return lo | (spread4(qh >> e0) << 4);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+template <> struct Block<T_Q5_1> {  // dequant.py:71-85   [d][m][qh u32][qs 16]
+    static constexpr int BS = 32, TS = 24, BIAS = 0, KIND = 1, A_BLK = 8;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        uint32_t qh = ld32<4>(b + 4);
+        uint32_t lo = (ld32<4>(b + 8 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
+        return lo | (spread4(qh >> e0) << 4);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+template <> struct Block<T_Q8_0> {  // dequant.py:65-69   [d][int8 x 32]
+    static constexpr int BS = 32, TS = 34, BIAS = 128, KIND = 0, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0) { return ld32<2>(b + 2 + e0) ^ 0x80808080u; }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+template <> struct Block<T_IQ4_NL> {  // dequant.py:243-256   layout of Q4_0, values through the table
+    static constexpr int BS = 32, TS = 18, BIAS = 127, KIND = 0, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        return iq4_lookup4((ld32<2>(b + 2 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+};
+
+// ---------------------------------------------------------------- K-quants, 256-element super-blocks
+// dequant.py:129-139: eight 6-bit (scale, min) pairs in 12 bytes s[0..11]
+template <int A> __device__ __forceinline__ void k_scale_min(const uint8_t *s, int j, int &sc, int &mn)
+{
+    if (j < 4) {
+        sc = s[j] & 63;
+        mn = s[j + 4] & 63;
+    } else {
+        sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4);
+        mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4);
+    }
+}
+
+template <> struct Block<T_Q2_K> {  // dequant.py:221-238   [scales 16][qs 64][d][dmin]
+    static constexpr int BS = 256, TS = 84, BIAS = 0, KIND = 3, A_BLK = 4;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<4>(b + 80); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 82); }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        return (ld32<4>(b + 16 + 32 * (e0 >> 7) + (e0 & 31)) >> (2 * ((e0 >> 5) & 3))) & 0x03030303u;
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        uint32_t s = b[e0 >> 4];
+        sc = s & 0x0F;
+        mn = s >> 4;
+    }
+};
+template <> struct Block<T_Q3_K> {  // dequant.py:197-219   [hmask 32][qs 64][scales 12][d]
+    static constexpr int BS = 256, TS = 110, BIAS = 4, KIND = 2, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 108); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        uint32_t lo = (ld32<2>(b + 32 + 32 * (e0 >> 7) + (e0 & 31)) >> (2 * ((e0 >> 5) & 3))) & 0x03030303u;
+        uint32_t hb = (ld32<2>(b + (e0 & 31)) >> (e0 >> 5)) & 0x01010101u;
+        return lo + (hb << 2);  // q = lo - 4*(hb^1) = lo + 4*hb - 4
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        int i = e0 >> 4;
+        uint32_t ls = (b[96 + (i & 7)] >> (4 * (i >> 3))) & 0x0F;
+        uint32_t hs = (b[104 + (i & 3)] >> (2 * (i >> 2))) & 3;
+        sc = (int)(ls | (hs << 4)) - 32;
+        mn = 0;
+    }
+};
+template <> struct Block<T_Q4_K> {  // dequant.py:180-195   [d][dmin][scales 12][qs 128]
+    static constexpr int BS = 256, TS = 144, BIAS = 0, KIND = 3, A_BLK = 16;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        return (ld32<4>(b + 16 + 32 * (e0 >> 6) + (e0 & 31)) >> (4 * ((e0 >> 5) & 1))) & 0x0F0F0F0Fu;
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        k_scale_min<4>(b + 4, e0 >> 5, sc, mn);
+    }
+};
+template <> struct Block<T_Q5_K> {  // dequant.py:159-178   [d][dmin][scales 12][qh 32][qs 128]
+    static constexpr int BS = 256, TS = 176, BIAS = 0, KIND = 3, A_BLK = 16;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        int sb = e0 >> 5;
+        uint32_t lo = (ld32<4>(b + 48 + 32 * (e0 >> 6) + (e0 & 31)) >> (4 * (sb & 1))) & 0x0F0F0F0Fu;
+        uint32_t hi = (ld32<4>(b + 16 + (e0 & 31)) >> sb) & 0x01010101u;
+        return lo | (hi << 4);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        k_scale_min<4>(b + 4, e0 >> 5, sc, mn);
+    }
+};
+template <> struct Block<T_Q6_K> {  // dequant.py:141-157   [ql 128][qh 64][scales i8 16][d]
+    static constexpr int BS = 256, TS = 210, BIAS = 32, KIND = 2, A_BLK = 2;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 208); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        int h = e0 >> 7, r = e0 & 127;
+        uint32_t lo = (ld32<2>(b + 64 * h + (r & 63)) >> (4 * (r >> 6))) & 0x0F0F0F0Fu;
+        uint32_t hi = (ld32<2>(b + 128 + 32 * h + (r & 31)) >> (2 * (r >> 5))) & 0x03030303u;
+        return lo | (hi << 4);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        sc = (int)(int8_t)b[192 + (e0 >> 4)];
+        mn = 0;
+    }
+};
+template <> struct Block<T_IQ4_XS> {  // dequant.py:258-285   [d][scales_h u16][scales_l 4][qs 128]
+    static constexpr int BS = 256, TS = 136, BIAS = 127, KIND = 2, A_BLK = 8;
+    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
+    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
+    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    {
+        int i = e0 >> 5;
+        uint32_t idx = (ld32<4>(b + 8 + 16 * i + (e0 & 15)) >> (4 * ((e0 >> 4) & 1))) & 0x0F0F0F0Fu;
+        return iq4_lookup4(idx);
+    }
+    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    {
+        int i = e0 >> 5;
+        uint32_t sh = ld16<2>(b + 2);
+        uint32_t ls = (b[4 + (i >> 1)] >> (4 * (i & 1))) & 0x0F;
+        uint32_t hs = (sh >> (2 * i)) & 3;
+        sc = (int)(ls | (hs << 4)) - 32;
+        mn = 0;
+    }
+};
+
+// ---------------------------------------------------------------- float step shared by every consumer
+// N consecutive elements (N = 4 or 8, e0 % N == 0) of one block -> N/2 pairs in the math dtype,
+// op order and per-op rounding exactly as the reference (see oracle/gguf_oracle.c::float_step).
+template <class Q, int MATH, int N>
+__device__ __forceinline__ void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
+{
+    using M = Math<MATH>;
+    static_assert(N == 4 || N == 8, "run length");
+    typename M::T d = M::from_h(Q::d_bits(blk));
+    typename M::T2 a, b;
+    if constexpr (Q::KIND == 0) {
+        a = M::bcast(d);
+    } else if constexpr (Q::KIND == 1) {
+        a = M::bcast(d);
+        b = M::bcast(M::from_h(Q::d2_bits(blk)));
+    } else {
+        int sc, mn;
+        Q::scales(blk, e0, sc, mn);
+        a = M::bcast(M::mul(d, M::from_int(sc)));
+        if constexpr (Q::KIND == 3) b = M::bcast(M::mul(M::from_h(Q::d2_bits(blk)), M::from_int(mn)));
+    }
+#pragma unroll
+    for (int j = 0; j < N / 4; ++j) {
+        typename M::T2 lo, hi;
+        M::cvt4(Q::q4(blk, e0 + 4 * j), Q::BIAS, lo, hi);
+        lo = M::mul2(a, lo);
+        hi = M::mul2(a, hi);
+        if constexpr (Q::KIND == 1) {
+            lo = M::add2(lo, b);
+            hi = M::add2(hi, b);
+        } else if constexpr (Q::KIND == 3) {
+            lo = M::sub2(lo, b);
+            hi = M::sub2(hi, b);
+        }
+        out[2 * j] = lo;
+        out[2 * j + 1] = hi;
+    }
+}
+
+}  // namespace ggufb200

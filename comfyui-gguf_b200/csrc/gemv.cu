@@ -1,0 +1,200 @@
+// gemv.cu -- K3: small-M fused dequant + dot product  Y[m,n] = sum_k X[m,k] * W[n,k] (+bias).
+//
+// For M <= 8 (modulation / adaLN / time-embedding Linears at batch 1..8) the Linear is bound by
+// reading the PACKED weight once from HBM; the weight is never materialised.  One warp owns an
+// output feature n, lanes stride the row in runs of 8 consecutive k (one 16-byte X vector per m),
+// the packed bytes are read straight from global memory through the shared blocks.cuh unpackers,
+// W is rounded to the activation dtype exactly as the reference does before F.linear
+// (dequant.py:23, ops.py:210) and accumulated in fp32; warp-shuffle reduction at the end.
+#include "blocks.cuh"
+
+namespace ggufb200 {
+
+constexpr int kGemvThreads = 256;
+constexpr int kGemvMaxM = 8;
+
+int gemv_max_m() { return kGemvMaxM; }
+
+template <int ACT> __device__ __forceinline__ float2 act_bits_to_f32x2(uint32_t b)
+{
+    if constexpr (ACT == kBF16) return make_float2(__uint_as_float(b << 16), __uint_as_float(b & 0xFFFF0000u));
+    else return __half22float2(*reinterpret_cast<__half2 *>(&b));
+}
+
+// bias value rounded to the activation dtype first: the reference casts the bias to x.dtype
+// (ops.py:205-207, bias_dtype = dtype) before F.linear adds it
+template <int ACT> __device__ __forceinline__ float load_bias(const void *bias, int bias_dtype, long long n)
+{
+    float b;
+    if (bias_dtype == kF32) b = reinterpret_cast<const float *>(bias)[n];
+    else if (bias_dtype == kF16) b = __half2float(reinterpret_cast<const __half *>(bias)[n]);
+    else b = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(bias)[n]);
+    if constexpr (ACT == kBF16) return __bfloat162float(__float2bfloat16_rn(b));
+    else return __half2float(__float2half_rn(b));
+}
+
+template <class Q, int MATH, int ACT, int MM>
+__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const uint8_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
+                                                            long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
+                                                            uint8_t *__restrict__ Y, long long ldy)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * kGemvThreads + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * kGemvThreads) >> 5;
+    const long long row_bytes = K / Q::BS * Q::TS;
+
+    for (long long n = warp; n < N; n += n_warps) {
+        const uint8_t *wrow = W + n * row_bytes;
+        float acc[MM];
+#pragma unroll
+        for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
+
+        for (long long k = lane * 8; k < K; k += 256) {
+            typename Math<MATH>::T2 v[4];
+            dequant_run<Q, MATH, 8>(wrow + (k / Q::BS) * Q::TS, (int)(k % Q::BS), v);
+            float2 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = act_bits_to_f32x2<ACT>(pack16<ACT, MATH>(v[j]));
+#pragma unroll
+            for (int m = 0; m < MM; ++m) {
+                if (m < M) {
+                    const uint4 xv = *reinterpret_cast<const uint4 *>(X + ((long long)m * ldx + k) * 2);
+                    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 xf = act_bits_to_f32x2<ACT>(xs[j]);
+                        acc[m] = fmaf(w[j].x, xf.x, acc[m]);
+                        acc[m] = fmaf(w[j].y, xf.y, acc[m]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MM; ++m) {
+            float a = acc[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && m < M) {
+                if (bias) a += load_bias<ACT>(bias, bias_dtype, n);
+                if constexpr (ACT == kBF16) reinterpret_cast<__nv_bfloat16 *>(Y)[(long long)m * ldy + n] = __float2bfloat16_rn(a);
+                else reinterpret_cast<__half *>(Y)[(long long)m * ldy + n] = __float2half_rn(a);
+            }
+        }
+    }
+}
+
+// BF16-typed weight (is_quantized() is true for BF16, dequant.py:7): W -> fp32 -> act dtype
+template <int ACT, int MM>
+__global__ void __launch_bounds__(kGemvThreads) gemv_bf16w_kernel(const uint16_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
+                                                                  long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
+                                                                  uint8_t *__restrict__ Y, long long ldy)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * kGemvThreads + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * kGemvThreads) >> 5;
+    for (long long n = warp; n < N; n += n_warps) {
+        float acc[MM];
+#pragma unroll
+        for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
+        for (long long k = lane; k < K; k += 32) {
+            float w = __uint_as_float((uint32_t)W[n * K + k] << 16);
+            if constexpr (ACT == kF16) w = __half2float(__float2half_rn(w));
+#pragma unroll
+            for (int m = 0; m < MM; ++m) {
+                if (m < M) {
+                    uint16_t xb = reinterpret_cast<const uint16_t *>(X)[(long long)m * ldx + k];
+                    float xf = ACT == kBF16 ? __uint_as_float((uint32_t)xb << 16) : __half2float(__ushort_as_half(xb));
+                    acc[m] = fmaf(w, xf, acc[m]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MM; ++m) {
+            float a = acc[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0 && m < M) {
+                if (bias) a += load_bias<ACT>(bias, bias_dtype, n);
+                if constexpr (ACT == kBF16) reinterpret_cast<__nv_bfloat16 *>(Y)[(long long)m * ldy + n] = __float2bfloat16_rn(a);
+                else reinterpret_cast<__half *>(Y)[(long long)m * ldy + n] = __float2half_rn(a);
+            }
+        }
+    }
+}
+
+static unsigned gemv_grid(long long N)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (N + 7) / 8;
+    long long cap = (long long)sms * 8;
+    return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+template <class Q, int MATH, int ACT>
+static int gemv_launch(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
+                       void *Y, long long ldy, cudaStream_t st)
+{
+    const uint8_t *w = reinterpret_cast<const uint8_t *>(W);
+    const uint8_t *x = reinterpret_cast<const uint8_t *>(X);
+    uint8_t *y = reinterpret_cast<uint8_t *>(Y);
+    unsigned grid = gemv_grid(N);
+    if (M <= 1) gemv_kernel<Q, MATH, ACT, 1><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+    else if (M <= 2) gemv_kernel<Q, MATH, ACT, 2><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+    else if (M <= 4) gemv_kernel<Q, MATH, ACT, 4><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+    else gemv_kernel<Q, MATH, ACT, 8><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+    return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <class Q, int MATH>
+static int gemv_act(const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, const void *bias, int bias_dtype,
+                    void *Y, long long ldy, cudaStream_t st)
+{
+    if (act == kBF16) return gemv_launch<Q, MATH, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
+    return gemv_launch<Q, MATH, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
+}
+
+template <class Q>
+static int gemv_math(const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, int math, const void *bias,
+                     int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    switch (math) {
+    case kF16: return gemv_act<Q, kF16>(W, N, K, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
+    case kBF16: return gemv_act<Q, kBF16>(W, N, K, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
+    case kF32: return gemv_act<Q, kF32>(W, N, K, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
+    }
+    return GGUFB200_E_DTYPE;
+}
+
+int gemv_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype, int math_dtype,
+                  const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    if (M > kGemvMaxM) return GGUFB200_E_SHAPE;
+    switch (type) {
+    case T_Q4_0: return gemv_math<Block<T_Q4_0>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q4_1: return gemv_math<Block<T_Q4_1>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q5_0: return gemv_math<Block<T_Q5_0>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q5_1: return gemv_math<Block<T_Q5_1>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q8_0: return gemv_math<Block<T_Q8_0>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q2_K: return gemv_math<Block<T_Q2_K>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q3_K: return gemv_math<Block<T_Q3_K>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q4_K: return gemv_math<Block<T_Q4_K>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q5_K: return gemv_math<Block<T_Q5_K>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_Q6_K: return gemv_math<Block<T_Q6_K>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_IQ4_NL: return gemv_math<Block<T_IQ4_NL>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_IQ4_XS: return gemv_math<Block<T_IQ4_XS>>(W, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case T_BF16: {
+        const uint16_t *w = reinterpret_cast<const uint16_t *>(W);
+        const uint8_t *x = reinterpret_cast<const uint8_t *>(X);
+        uint8_t *y = reinterpret_cast<uint8_t *>(Y);
+        unsigned grid = gemv_grid(N);
+        if (act_dtype == kBF16) gemv_bf16w_kernel<kBF16, 8><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+        else gemv_bf16w_kernel<kF16, 8><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+        return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+    }
+    }
+    return GGUFB200_E_TYPE;
+}
+
+}  // namespace ggufb200

@@ -1,0 +1,305 @@
+"""Drop-in for the reference's ops.py -- the ComfyUI custom-operations surface, B200 kernels inside.
+
+Mirrored surface (reference file:line):
+    GGMLTensor      ops.py:44-91     tensor subclass carrying packed bytes + tensor_type/tensor_shape/patches
+    GGMLLayer       ops.py:93-225    state-dict hooks, get_weight, cast_bias_weight, forward dispatch
+    GGMLOps         ops.py:227-271   Linear / Conv2d / Embedding / LayerNorm / GroupNorm
+    move_patch_to_device  ops.py:273-281
+
+What changes underneath:
+    * Linear.forward_ggml_cast_weights (ops.py:242-244) no longer materialises W through ~17 ATen kernels and
+      then calls F.linear: it hands the PACKED weight to ggufb200_linear (fused dequant + GEMV / tcgen05 GEMM).
+      LoRA-patched weights, fp32 activations and CPU inputs take the two-step route (one dequant launch,
+      then comfy.lora.calculate_weight / F.linear) so their semantics stay those of the reference.
+    * get_weight (ops.py:166-191) dequantises with ONE kernel launch (dequant.py of this package).
+    * Embedding (ops.py:251-259) gathers only the indexed rows instead of dequantising the whole table.
+"""
+from __future__ import annotations
+
+import logging
+
+import gguf
+import torch
+
+from . import _lib
+from ._host import comfy_lora, comfy_mm, comfy_ops
+from .dequant import dequantize_rows, dequantize_tensor, dtype_code, is_quantized, math_code
+
+_Q = gguf.GGMLQuantizationType
+_FUSED_ACT = (torch.float16, torch.bfloat16)
+GEMV_MAX_M = 8   # csrc/gemv.cu kGemvMaxM
+
+
+def torch_compiler_disable(*_args, **_kwargs):
+    """ops.py:21-42: on torch >= 2.8 the reference lets torch.compile trace through; the kernels here are
+    reached through ctypes, which dynamo treats as an opaque call, so the guard is an identity decorator."""
+    def wrap(fn):
+        return fn
+    return wrap
+
+
+class GGMLTensor(torch.Tensor):
+    """Packed GGUF payload as a tensor (ops.py:44-91).  `.shape` is the LOGICAL shape; `.size()` the byte shape."""
+
+    def __new__(cls, data, *args, tensor_type, tensor_shape, patches=(), **kwargs):
+        return torch.Tensor._make_subclass(cls, data, False)
+
+    def __init__(self, data, *args, tensor_type, tensor_shape, patches=(), **kwargs):
+        self.tensor_type = tensor_type
+        self.tensor_shape = tensor_shape
+        self.patches = list(patches)
+
+    def _meta_onto(self, other):
+        other.tensor_type = getattr(self, "tensor_type", None)
+        other.tensor_shape = getattr(self, "tensor_shape", other.data.shape)
+        other.patches = list(getattr(self, "patches", []))
+        return other
+
+    def to(self, *args, **kwargs):
+        return self._meta_onto(super().to(*args, **kwargs))
+
+    def clone(self, *args, **kwargs):
+        return self  # nn.Parameter(GGMLTensor) must stay the same object (ops.py:64-68, 124)
+
+    def detach(self, *args, **kwargs):
+        return self
+
+    def copy_(self, *args, **kwargs):
+        try:
+            return super().copy_(*args, **kwargs)
+        except Exception as exc:  # ops.py:70-75: CLIP text models call weight.copy_ with logical shapes
+            logging.warning(f"ignoring 'copy_' on tensor: {exc}")
+
+    def new_empty(self, size, *args, **kwargs):
+        fresh = super().new_empty(size, *args, **kwargs)
+        return GGMLTensor(fresh, tensor_type=getattr(self, "tensor_type", None), tensor_shape=size,
+                          patches=list(getattr(self, "patches", [])))
+
+    @property
+    def shape(self):
+        if not hasattr(self, "tensor_shape"):
+            self.tensor_shape = self.size()
+        return self.tensor_shape
+
+
+def move_patch_to_device(item, device):
+    """ops.py:273-281."""
+    if isinstance(item, torch.Tensor):
+        return item.to(device, non_blocking=True)
+    if isinstance(item, tuple):
+        return tuple(move_patch_to_device(x, device) for x in item)
+    if isinstance(item, list):
+        return [move_patch_to_device(x, device) for x in item]
+    return item
+
+
+def _plain(t):
+    return t.as_subclass(torch.Tensor) if isinstance(t, GGMLTensor) else t
+
+
+def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
+    """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.
+
+    x: CUDA fp16/bf16 [..., K]; weight: CUDA GGMLTensor (quantised type); bias: None or a CUDA tensor
+    (fp32 / fp16 / bf16, rounded to x.dtype inside the kernel exactly like ops.py:205-207 does)."""
+    qtype = weight.tensor_type
+    N, K = tuple(weight.tensor_shape)
+    if x.shape[-1] != K:
+        raise ValueError(f"linear_packed: input features {x.shape[-1]} != weight in_features {K}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    wraw = _plain(weight)
+    if not wraw.is_contiguous():
+        wraw = wraw.contiguous()
+    act = dtype_code(x.dtype)
+    bias_ptr, bias_code = None, 0
+    if bias is not None:
+        bias = _plain(bias)
+        if not bias.is_contiguous():
+            bias = bias.contiguous()
+        bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
+    L = _lib.lib()
+    ws, ws_ptr, ws_bytes = None, None, 0
+    need = L.ggufb200_linear_workspace(int(qtype), M, N, K, act, algo)
+    if need:
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        ws_ptr, ws_bytes = ws.data_ptr(), need
+    with torch.cuda.device(x.device):
+        rc = L.ggufb200_linear(int(qtype), wraw.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act,
+                               math_code(dequant_dtype, x.dtype), bias_ptr, bias_code, y.data_ptr(), N, ws_ptr, ws_bytes, algo,
+                               torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, f"ggufb200_linear({getattr(qtype, 'name', qtype)}, M={M}, N={N}, K={K})")
+    return y.reshape(*x.shape[:-1], N)
+
+
+class GGMLLayer(torch.nn.Module):
+    """On-the-fly dequantising layer base (ops.py:93-225)."""
+    comfy_cast_weights = True
+    dequant_dtype = None
+    patch_dtype = None
+    largest_layer = False
+    torch_compatible_tensor_types = {None, _Q.F32, _Q.F16}
+
+    def is_ggml_quantized(self, *, weight=None, bias=None):
+        weight = self.weight if weight is None else weight
+        bias = self.bias if bias is None else bias
+        return is_quantized(weight) or is_quantized(bias)
+
+    # ---- state dict plumbing (ops.py:110-164)
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        weight, bias = state_dict.get(f"{prefix}weight"), state_dict.get(f"{prefix}bias")
+        if self.is_ggml_quantized(weight=weight, bias=bias) or isinstance(self, torch.nn.Linear):
+            return self.ggml_load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        if isinstance(self, torch.nn.Embedding) and self.weight.shape[0] >= (64 * 1024):
+            return self.ggml_load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def ggml_load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        plen = len(prefix)
+        for key, value in state_dict.items():
+            name = key[plen:]
+            if name == "weight":
+                self.weight = torch.nn.Parameter(value, requires_grad=False)
+            elif name == "bias" and value is not None:
+                self.bias = torch.nn.Parameter(value, requires_grad=False)
+            else:
+                unexpected_keys.append(key)
+        if self.weight is None and isinstance(self, torch.nn.Linear):  # ops.py:131-134
+            self.weight = torch.nn.Parameter(torch.zeros(self.in_features, self.out_features), requires_grad=False)
+            missing_keys.append(prefix + "weight")
+        if getattr(self.weight, "is_largest_weight", False):  # ops.py:136-138
+            self.largest_layer = True
+
+    def _save_to_state_dict(self, *args, **kwargs):
+        if self.is_ggml_quantized():
+            return self.ggml_save_to_state_dict(*args, **kwargs)
+        return super()._save_to_state_dict(*args, **kwargs)
+
+    def ggml_save_to_state_dict(self, destination, prefix, keep_vars):
+        """Meta-device stand-ins used by the host for VRAM estimation (ops.py:140-160)."""
+        meta = torch.device("meta")
+        destination[prefix + "weight"] = torch.zeros_like(self.weight, device=meta)
+        if self.bias is not None:
+            destination[prefix + "bias"] = torch.zeros_like(self.bias, device=meta)
+        if self.largest_layer:
+            # scratch the two-step route needs for the largest dequantised weight
+            shape = getattr(self.weight, "tensor_shape", self.weight.shape)
+            dt = self.dequant_dtype if self.dequant_dtype and self.dequant_dtype != "target" else torch.float16
+            destination[prefix + "temp.weight"] = torch.empty(*shape, device=meta, dtype=dt)
+
+    # ---- weight materialisation (ops.py:166-211)
+    def get_weight(self, tensor, dtype):
+        if tensor is None:
+            return None
+        patch_list, key = [], None
+        for patches, key in getattr(tensor, "patches", []):
+            patch_list += move_patch_to_device(patches, tensor.device)
+        weight = dequantize_tensor(tensor, dtype, self.dequant_dtype)   # one kernel launch
+        weight = _plain(weight)
+        if patch_list:
+            if self.patch_dtype is None:
+                weight = comfy_lora.calculate_weight(patch_list, weight, key)
+            else:
+                pdt = dtype if self.patch_dtype == "target" else self.patch_dtype
+                weight = comfy_lora.calculate_weight(patch_list, weight, key, pdt)
+        return weight
+
+    @torch_compiler_disable()
+    def cast_bias_weight(s, input=None, dtype=None, device=None, bias_dtype=None):
+        if input is not None:
+            if dtype is None:
+                dtype = getattr(input, "dtype", torch.float32)
+            if bias_dtype is None:
+                bias_dtype = dtype
+            if device is None:
+                device = input.device
+        non_blocking = comfy_mm.device_supports_non_blocking(device)
+        bias = None
+        if s.bias is not None:
+            bias = s.get_weight(s.bias.to(device), dtype)
+            bias = comfy_ops.cast_to(bias, bias_dtype, device, non_blocking=non_blocking, copy=False)
+        weight = s.get_weight(s.weight.to(device), dtype)
+        weight = comfy_ops.cast_to(weight, dtype, device, non_blocking=non_blocking, copy=False)
+        return weight, bias
+
+    def forward_comfy_cast_weights(self, input, *args, **kwargs):
+        if self.is_ggml_quantized():
+            out = self.forward_ggml_cast_weights(input, *args, **kwargs)
+        else:
+            out = super().forward_comfy_cast_weights(input, *args, **kwargs)
+        return _plain(out)
+
+    def forward_ggml_cast_weights(self, input):
+        raise NotImplementedError
+
+
+class GGMLOps(comfy_ops.manual_cast):
+    """`custom_operations` object handed to comfy.sd loaders (ops.py:227-271)."""
+
+    class Linear(GGMLLayer, comfy_ops.manual_cast.Linear):
+        def __init__(self, in_features, out_features, bias=True, device=None, dtype=None):
+            torch.nn.Module.__init__(self)   # allocates nothing (ops.py:232-240)
+            self.in_features = in_features
+            self.out_features = out_features
+            self.weight = None
+            self.bias = None
+
+        def _fused_ok(self, input):
+            w = self.weight
+            return (input.is_cuda and input.dtype in _FUSED_ACT and is_quantized(w) and not getattr(w, "patches", None)
+                    and not is_quantized(self.bias) and len(getattr(w, "tensor_shape", ())) == 2
+                    and not getattr(self.bias, "patches", None))
+
+        def forward_ggml_cast_weights(self, input):
+            if self._fused_ok(input):
+                dev = input.device
+                w = self.weight if self.weight.device == dev else self.weight.to(dev)   # offloaded module: packed bytes H2D
+                b = self.bias
+                if b is not None and b.device != dev:
+                    b = b.to(dev)
+                M = input.numel() // input.shape[-1]
+                if M <= GEMV_MAX_M or _lib.lib().ggufb200_supported(int(w.tensor_type), _lib.OP_LINEAR_MMA):
+                    return linear_packed(input, w, b, self.dequant_dtype)
+            weight, bias = self.cast_bias_weight(input)
+            return torch.nn.functional.linear(input, weight, bias)
+
+    class Conv2d(GGMLLayer, comfy_ops.manual_cast.Conv2d):
+        def forward_ggml_cast_weights(self, input):
+            weight, bias = self.cast_bias_weight(input)
+            return self._conv_forward(input, weight, bias)
+
+    class Embedding(GGMLLayer, comfy_ops.manual_cast.Embedding):
+        def forward_ggml_cast_weights(self, input, out_dtype=None):
+            want = out_dtype
+            if self.weight.dtype in (torch.float16, torch.bfloat16):
+                out_dtype = None
+            w = self.weight
+            plain_case = (self.max_norm is None and not getattr(w, "patches", None) and input.is_cuda
+                          and len(getattr(w, "tensor_shape", ())) == 2)
+            if plain_case:
+                w = w if w.device == input.device else w.to(input.device)
+                # the reference passes the module itself as `input` to cast_bias_weight (ops.py:256), so a missing
+                # out_dtype resolves to float32 there
+                row_dtype = torch.float32 if out_dtype is None else out_dtype
+                rows = dequantize_rows(w, input, row_dtype, self.dequant_dtype)
+                if self.padding_idx is not None:
+                    pass  # padding_idx only affects gradients in F.embedding
+                return rows.to(dtype=want)
+            weight, _bias = self.cast_bias_weight(self, device=input.device, dtype=out_dtype)
+            return torch.nn.functional.embedding(input, weight, self.padding_idx, self.max_norm, self.norm_type,
+                                                 self.scale_grad_by_freq, self.sparse).to(dtype=want)
+
+    class LayerNorm(GGMLLayer, comfy_ops.manual_cast.LayerNorm):
+        def forward_ggml_cast_weights(self, input):
+            if self.weight is None:
+                return super().forward_comfy_cast_weights(input)
+            weight, bias = self.cast_bias_weight(input)
+            return torch.nn.functional.layer_norm(input, self.normalized_shape, weight, bias, self.eps)
+
+    class GroupNorm(GGMLLayer, comfy_ops.manual_cast.GroupNorm):
+        def forward_ggml_cast_weights(self, input):
+            weight, bias = self.cast_bias_weight(input)
+            return torch.nn.functional.group_norm(input, self.num_groups, weight, bias, self.eps)

@@ -1,0 +1,137 @@
+/*
+ * ggufb200.h -- C ABI of libggufb200.so: B200 (sm_100a) GGUF block dequant and the
+ * Linear that consumes the dequantised weight.
+ *
+ * This is the drop-in boundary for the hot path of city96/ComfyUI-GGUF.  The
+ * reference has no native code, so each entry point names the PYTHON function it
+ * replaces (reference file:line); INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the
+ *     caller (PyTorch); the library never allocates, frees or retains device memory
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream)
+ *   - all calls are asynchronous on `stream`, re-entrant and hold no mutable global state
+ *   - return value: 0 = GGUFB200_OK, negative = error (ggufb200_strerror()); no C++
+ *     exception crosses the boundary
+ *   - ggml_type uses gguf-py's GGMLQuantizationType integer values
+ *     (Q4_0=2 Q4_1=3 Q5_0=6 Q5_1=7 Q8_0=8 Q2_K=10 Q3_K=11 Q4_K=12 Q5_K=13 Q6_K=14
+ *      IQ4_NL=20 IQ4_XS=23 BF16=30), i.e. the keys of dequant.py:287-301
+ *   - dtype codes: 0 = float16, 1 = bfloat16, 2 = float32
+ */
+#ifndef GGUFB200_H
+#define GGUFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGUFB200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* error codes */
+#define GGUFB200_OK 0
+#define GGUFB200_E_TYPE (-1)      /* ggml_type not in dequant.py:287-301 */
+#define GGUFB200_E_DTYPE (-2)     /* dtype code out of range */
+#define GGUFB200_E_ALIGN (-3)     /* output / activation pointer not 16-byte aligned */
+#define GGUFB200_E_SHAPE (-4)     /* K not a multiple of the block size, negative size, ld too small ... */
+#define GGUFB200_E_NULL (-5)      /* required pointer is NULL */
+#define GGUFB200_E_CUDA (-6)      /* a CUDA call failed (cudaGetLastError preserved for the caller) */
+#define GGUFB200_E_WORKSPACE (-7) /* workspace smaller than ggufb200_linear_workspace() */
+#define GGUFB200_E_UNSUPPORTED (-8) /* op / dtype combination not implemented for this type */
+#define GGUFB200_E_DEVICE (-9)    /* current device is not sm_100 */
+
+/* dtype codes */
+#define GGUFB200_F16 0
+#define GGUFB200_BF16 1
+#define GGUFB200_F32 2
+
+/* op codes for ggufb200_supported() */
+#define GGUFB200_OP_DEQUANT 0
+#define GGUFB200_OP_LINEAR 1
+#define GGUFB200_OP_ROWS 2
+#define GGUFB200_OP_LINEAR_MMA 3 /* large-M tcgen05 path (fused or dequant+GEMM) available for this type */
+
+/* algorithm selector for ggufb200_linear() */
+#define GGUFB200_ALGO_AUTO 0
+#define GGUFB200_ALGO_GEMV 1        /* small-M fused dequant + dot product (CUDA cores, HBM-read bound) */
+#define GGUFB200_ALGO_FUSED_MMA 2   /* fused dequant -> smem -> tcgen05.mma, accumulators in TMEM */
+#define GGUFB200_ALGO_DEQUANT_MMA 3 /* dequant into the caller's workspace, then the tcgen05 GEMM on it */
+
+int ggufb200_version(void);
+const char *ggufb200_strerror(int rc);
+
+/* Block geometry: replaces gguf.GGML_QUANT_SIZES[qtype] as used at dequant.py:34. */
+int ggufb200_type_info(int ggml_type, int *block_size, int *type_size);
+
+/* 1 if (ggml_type, op) is implemented, else 0.  Mirrors `qtype in dequantize_functions`
+ * (dequant.py:21, 287-301).  There is no CPU/numpy fallback (dequant.py:24-28 is NOT reproduced). */
+int ggufb200_supported(int ggml_type, int op);
+
+/*
+ * Standalone dequant.  Replaces dequant.py:30-44 `dequantize()` + the per-type
+ * `dequantize_blocks_*` (dequant.py:61-285) + the final `.to(dtype)` (dequant.py:23).
+ *   packed     n_blocks * type_size bytes, block b covers out[b*block_size .. +block_size)
+ *   out        n_blocks * block_size elements of out_dtype, 16-byte aligned
+ *   math_dtype dtype the float ops run in and round to after every op: 0 (fp16) is the
+ *              reference default (`dequant_dtype=None`), the activation dtype reproduces
+ *              `dequant_dtype="target"`, 2 an explicit float32.  Results are bit-identical
+ *              to the reference for every (math_dtype, out_dtype) pair.
+ */
+int ggufb200_dequant(int ggml_type, const void *packed, int64_t n_blocks, void *out, int out_dtype,
+                     int math_dtype, void *stream);
+
+/*
+ * Integer unpack only (test/debug surface for the "bit-exact integer unpack" contract):
+ * per element the integer quant value q as it enters the float multiply, the integer
+ * sub-block scale sc (1 if the type has none) and min mn (0 if none).  Any of the three
+ * int16 output arrays (n_blocks*block_size each) may be NULL.
+ */
+int ggufb200_unpack_int(int ggml_type, const void *packed, int64_t n_blocks, int16_t *q, int16_t *sc,
+                        int16_t *mn, void *stream);
+
+/*
+ * Row gather + dequant: out[i, :] = dequant(W[rows[i], :]).  Replaces the
+ * "dequantise the whole table, then F.embedding" of ops.py:251-259 for quantised
+ * Embedding weights.  rows: n_rows int64 indices on the device; K = logical row length.
+ */
+int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_rows, int64_t K,
+                          const int64_t *rows, int64_t n_rows, void *out, int out_dtype, int math_dtype,
+                          void *stream);
+
+/*
+ * Fused Linear: Y[M,N] = X[M,K] * dequant(W)[N,K]^T (+ bias[N]).  Replaces
+ * ops.py:242-244 `forward_ggml_cast_weights` = cast_bias_weight (ops.py:193-211)
+ * -> get_weight/dequantize_tensor (ops.py:166-191) -> F.linear.
+ *   W_packed    N rows of K/block_size*type_size bytes (loader.py:118-120 layout)
+ *   X, Y        act_dtype (0 fp16 / 1 bf16), row strides ldx / ldy in ELEMENTS, 16-byte aligned
+ *   math_dtype  as in ggufb200_dequant(): W is first produced in math_dtype with the
+ *               reference's rounding sequence and then cast to act_dtype, exactly the
+ *               weight the reference hands to F.linear; accumulation is fp32
+ *   bias        NULL or N values of bias_dtype (0/1/2)
+ *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0)
+ *   algo        GGUFB200_ALGO_*
+ */
+size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo);
+
+int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M,
+                    int64_t ldx, int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y,
+                    int64_t ldy, void *workspace, size_t workspace_bytes, int algo, void *stream);
+
+/*
+ * Plain tensor-core GEMM on an already-dense weight: Y = X * W^T (+bias), W[N,K] in
+ * act_dtype.  Used for the F16/BF16 (torch-compatible) Linears of a model and as the
+ * second half of GGUFB200_ALGO_DEQUANT_MMA.
+ */
+int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx,
+                  int act_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream);
+
+/* Tuning knob for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default). */
+int ggufb200_set_tuning(int key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGUFB200_H */

@@ -1,0 +1,72 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/ggufb200.h declares, and validates arguments
+before touching the GPU (so these checks run without a device)."""
+import ctypes
+import os
+import re
+
+import gguf
+import pytest
+
+from util import ALL_QTYPES, Q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported(pkg):
+    header = open(os.path.join(ROOT, "include", "ggufb200.h")).read()
+    declared = set(re.findall(r"\b(ggufb200_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 10
+    L = pkg.lib.lib()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"{sym} declared in include/ggufb200.h but not exported"
+    assert declared == set(pkg.lib.EXPORTS)
+
+
+def test_version_and_strerror(pkg):
+    L = pkg.lib.lib()
+    assert L.ggufb200_version() == 100
+    assert L.ggufb200_strerror(0) == b"ok"
+    for rc in range(-9, 0):
+        assert len(L.ggufb200_strerror(rc)) > 3
+
+
+@pytest.mark.parametrize("qt", ALL_QTYPES, ids=lambda q: q.name)
+def test_type_info_matches_gguf_py(pkg, qt):
+    bs, ts = ctypes.c_int(), ctypes.c_int()
+    assert pkg.lib.lib().ggufb200_type_info(int(qt), ctypes.byref(bs), ctypes.byref(ts)) == 0
+    assert (bs.value, ts.value) == gguf.GGML_QUANT_SIZES[qt]
+    assert pkg.lib.lib().ggufb200_supported(int(qt), pkg.lib.OP_DEQUANT) == 1
+
+
+def test_supported_set_equals_reference_table(pkg):
+    """dequant.py:287-301 lists exactly these 13 types; anything else must be rejected (no numpy fallback)."""
+    L = pkg.lib.lib()
+    supported = {int(q) for q in Q if L.ggufb200_supported(int(q), 0)}
+    assert supported == {int(q) for q in ALL_QTYPES}
+    assert set(pkg.dequant.dequantize_functions.keys()) == set(ALL_QTYPES)
+
+
+def test_argument_validation_without_gpu(pkg):
+    L = pkg.lib.lib()
+    buf = (ctypes.c_uint8 * 4096)()
+    p = ctypes.addressof(buf)
+    p16 = (p + 15) & ~15
+    assert L.ggufb200_dequant(999, p16, 1, p16, 0, 0, None) == -1          # E_TYPE
+    assert L.ggufb200_dequant(int(Q.Q4_K), p16, 1, p16, 7, 0, None) == -2  # E_DTYPE
+    assert L.ggufb200_dequant(int(Q.Q4_K), p16, -1, p16, 0, 0, None) == -4  # E_SHAPE
+    assert L.ggufb200_dequant(int(Q.Q4_K), p16, 0, None, 0, 0, None) == 0   # empty input is fine
+    assert L.ggufb200_dequant(int(Q.Q4_K), None, 1, p16, 0, 0, None) == -5  # E_NULL
+    assert L.ggufb200_dequant(int(Q.Q4_K), p16, 1, p16 + 2, 0, 0, None) == -3  # E_ALIGN
+    # linear: K must be a multiple of the block size, act dtype must be 16-bit
+    assert L.ggufb200_linear(int(Q.Q4_K), p16, 8, 100, p16, 1, 100, 1, 0, None, 0, p16, 8, None, 0, 0, None) == -4
+    assert L.ggufb200_linear(int(Q.Q4_K), p16, 8, 256, p16, 1, 256, 2, 0, None, 0, p16, 8, None, 0, 0, None) == -2
+    assert L.ggufb200_linear(int(Q.Q4_K), p16, 8, 256, p16, 0, 256, 1, 0, None, 0, p16, 8, None, 0, 0, None) == 0
+    assert L.ggufb200_linear_workspace(int(Q.Q4_K), 64, 128, 256, 1, pkg.lib.ALGO_DEQUANT_MMA) == 128 * 256 * 2
+    assert L.ggufb200_linear_workspace(int(Q.Q4_K), 1, 128, 256, 1, pkg.lib.ALGO_GEMV) == 0
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    monkeypatch.setattr(pkg.lib, "_lib", None)
+    monkeypatch.setattr(pkg.lib, "LIB_PATH", "/nonexistent/libggufb200.so")
+    with pytest.raises(pkg.lib.GGUFB200Error):
+        pkg.lib.lib()

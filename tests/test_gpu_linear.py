@@ -1,0 +1,140 @@
+"""GPU parity tests of the Linear path (csrc/gemv.cu, csrc/gemm.cu) through the plugin surface.
+
+Tolerance (written here, from BASELINE.json north_star): ||y - y_ref||_F / ||y_ref||_F <= 1e-3 for fp16/bf16 Linear
+outputs; y_ref is the unmodified reference's GGMLOps.Linear output (golden files) or the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import gguf
+
+import oracle
+from util import Q, bits_to_f32, rel_fro, torch_bits
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-3
+
+
+def _weight(pkg, qt, N, K, seed=0, scale=0.02):
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    raw = oracle.random_blocks(int(qt), N * K // bs, seed=seed, scale=scale).reshape(N, K // bs * ts)
+    return raw, pkg.ops.GGMLTensor(torch.from_numpy(raw).to(DEV), tensor_type=qt, tensor_shape=torch.Size((N, K)))
+
+
+def _layer(pkg, qt, N, K, bias=True, seed=0):
+    raw, w = _weight(pkg, qt, N, K, seed)
+    lin = pkg.ops.GGMLOps.Linear(K, N)
+    sd = {"weight": w}
+    b = None
+    if bias:
+        b = np.random.default_rng(seed + 1).normal(0, 0.02, size=N).astype(np.float32)
+        sd["bias"] = pkg.ops.GGMLTensor(torch.from_numpy(b).to(DEV), tensor_type=Q.F32, tensor_shape=torch.Size((N,)))
+    lin.load_state_dict(sd)
+    return lin, raw, b
+
+
+@pytest.mark.parametrize("name", ["Q4_K", "Q8_0", "Q5_K", "Q6_K", "Q4_0", "BF16"])
+@pytest.mark.parametrize("act,code,dt", [("bf16", 1, torch.bfloat16), ("f16", 0, torch.float16), ("f32", 2, torch.float32)])
+def test_linear_matches_reference_ops_golden(pkg, name, act, code, dt, golden_dir):
+    """x (24 rows) through the drop-in GGMLOps.Linear vs the y the reference's GGMLOps.Linear produced."""
+    g = np.load(os.path.join(golden_dir, f"linear_{name}_{act}.npz"))
+    qt = Q(int(g["qtype"]))
+    N, K, M = int(g["N"]), int(g["K"]), int(g["M"])
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    lin = pkg.ops.GGMLOps.Linear(K, N)
+    w = pkg.ops.GGMLTensor(torch.from_numpy(g["packed"].reshape(N, K // bs * ts)).to(DEV), tensor_type=qt, tensor_shape=torch.Size((N, K)))
+    b = pkg.ops.GGMLTensor(torch.from_numpy(g["bias"]).to(DEV), tensor_type=Q.F32, tensor_shape=torch.Size((N,)))
+    lin.load_state_dict({"weight": w, "bias": b})
+    xb = g["x"]
+    x = torch.from_numpy(xb.view(np.float32) if code == 2 else xb.view(np.int16)).to(DEV)
+    x = x.view(dt).reshape(M, K)
+    want = bits_to_f32(g["y"], code)
+    for rows in (M, 5, 1):                       # M=24 -> large-M route, 5 and 1 -> fused GEMV
+        y = lin(x[:rows])
+        assert type(y) is torch.Tensor and y.dtype == dt and tuple(y.shape) == (rows, N)
+        got = y.float().cpu().numpy().reshape(-1)
+        assert rel_fro(got, want[: rows * N]) <= TOL, (name, act, rows)
+
+
+@pytest.mark.parametrize("qt", [Q.Q4_0, Q.Q4_1, Q.Q5_0, Q.Q5_1, Q.Q8_0, Q.Q2_K, Q.Q3_K, Q.Q4_K, Q.Q5_K, Q.Q6_K, Q.IQ4_NL, Q.IQ4_XS],
+                         ids=lambda q: q.name)
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_gemv_all_types_vs_oracle(pkg, qt, M):
+    N, K = 200, 1024
+    raw, w = _weight(pkg, qt, N, K, seed=int(qt))
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    bias = torch.randn(N, device=DEV, dtype=torch.float32) * 0.1
+    y = pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_GEMV)
+    bias_bits = torch_bits(bias.to(torch.bfloat16))
+    want = oracle.linear(raw, int(qt), N, K, torch_bits(x), oracle.DT_BF16, oracle.DT_F16, bias_bits)
+    assert rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), 1)) <= TOL
+
+
+def test_gemv_dequant_dtype_modes_and_fp16(pkg):
+    raw, w = _weight(pkg, Q.Q4_K, 128, 512, seed=5)
+    for act, code in ((torch.float16, 0), (torch.bfloat16, 1)):
+        x = torch.randn(2, 512, device=DEV, dtype=act)
+        for mode, mcode in ((None, 0), ("target", code), (torch.float32, 2)):
+            y = pkg.ops.linear_packed(x, w, None, mode, pkg.lib.ALGO_GEMV)
+            want = oracle.linear(raw, int(Q.Q4_K), 128, 512, torch_bits(x), code, mcode, None)
+            assert rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), code)) <= TOL
+
+
+def test_linear_strided_and_batched_input(pkg):
+    lin, raw, b = _layer(pkg, Q.Q8_0, 96, 256)
+    x = torch.randn(2, 3, 512, device=DEV, dtype=torch.bfloat16)[..., :256]   # non-contiguous rows, ld=512
+    y = lin(x)
+    assert tuple(y.shape) == (2, 3, 96)
+    W = pkg.dequant.dequantize_tensor(lin.weight, torch.bfloat16)
+    ref = torch.nn.functional.linear(x.float(), W.float(), torch.from_numpy(b).to(DEV).to(torch.bfloat16).float())
+    assert rel_fro(y.float().cpu().numpy(), ref.cpu().numpy()) <= 2e-3       # ref here is fp32 math on bf16 W: bf16 output rounding only
+
+
+def test_offloaded_weight_is_moved_packed(pkg):
+    """lowvram: module on the CPU, activations on the GPU -> packed bytes cross PCIe, result on the GPU (ops.py:209)."""
+    lin, raw, b = _layer(pkg, Q.Q4_K, 64, 512)
+    lin.weight = torch.nn.Parameter(lin.weight.to("cpu"), requires_grad=False)
+    x = torch.randn(4, 512, device=DEV, dtype=torch.float16)
+    y = lin(x)
+    want = oracle.linear(raw, int(Q.Q4_K), 64, 512, torch_bits(x), 0, 0, torch_bits(torch.from_numpy(b).to(torch.float16)))
+    assert y.is_cuda and rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), 0)) <= TOL
+
+
+def test_lora_patched_weight_takes_two_step_route(pkg):
+    """tensor.patches present -> dequant + comfy.lora.calculate_weight + F.linear, as the reference does (ops.py:171-190)."""
+    lin, raw, _ = _layer(pkg, Q.Q4_K, 64, 512, bias=False)
+    up = torch.randn(64, 4, device=DEV) * 0.05
+    down = torch.randn(4, 512, device=DEV) * 0.05
+    lin.weight.patches = [([(0.8, ("lora", (up, down, 2.0, None, None, None)), 1.0, None, None)], "w")]
+    x = torch.randn(6, 512, device=DEV, dtype=torch.bfloat16)
+    y = lin(x)
+    W = pkg.dequant.dequantize_tensor(lin.weight, torch.bfloat16).float()
+    Wp = (W.to(torch.bfloat16) + (0.8 * (2.0 / 4) * (up @ down)).to(torch.bfloat16)).float()
+    ref = torch.nn.functional.linear(x.float(), Wp)
+    assert rel_fro(y.float().cpu().numpy(), ref.cpu().numpy()) <= 3e-3
+    lin.weight.patches = []
+    y0 = lin(x)
+    assert rel_fro(y0.float().cpu().numpy(), torch.nn.functional.linear(x.float(), W).cpu().numpy()) <= 2e-3
+
+
+def test_embedding_row_gather_equals_reference_semantics(pkg):
+    emb = pkg.ops.GGMLOps.Embedding(500, 1024, device="meta")
+    raw, w = _weight(pkg, Q.Q5_K, 500, 1024, seed=8)
+    emb.load_state_dict({"weight": w}, assign=True)
+    idx = torch.tensor([[1, 499, 7, 7]], device=DEV)
+    full = pkg.dequant.dequantize_tensor(w, torch.float32)
+    out = emb(idx)
+    assert out.dtype == torch.float32 and torch.equal(out, torch.nn.functional.embedding(idx, full))
+    out16 = emb(idx, out_dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16
+    assert torch.equal(out16, torch.nn.functional.embedding(idx, pkg.dequant.dequantize_tensor(w, torch.bfloat16)))
+
+
+def test_error_paths_raise(pkg):
+    raw, w = _weight(pkg, Q.Q4_K, 32, 512)
+    with pytest.raises(ValueError):
+        pkg.ops.linear_packed(torch.randn(2, 256, device=DEV, dtype=torch.bfloat16), w, None)
+    with pytest.raises(pkg.lib.GGUFB200Error):
+        pkg.ops.linear_packed(torch.randn(64, 512, device=DEV, dtype=torch.bfloat16), w, None, None, pkg.lib.ALGO_GEMV)
