@@ -13,5 +13,5 @@ for f in api dequant rows gemv gemm; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libggufb200.so build/api.o build/dequant.o build/rows.o build/gemv.o build/gemm.o -lcuda
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libggufb200.so build/api.o build/dequant.o build/rows.o build/gemv.o build/gemm.o
 echo "built $(pwd)/libggufb200.so"

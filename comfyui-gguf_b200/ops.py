@@ -135,6 +135,28 @@ def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
     return y.reshape(*x.shape[:-1], N)
 
 
+def linear_dense(x, weight, bias=None):
+    """y = x @ weight.T + bias on the tcgen05 GEMM with an already dense fp16/bf16 weight (ggufb200_gemm)."""
+    N, K = weight.shape
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
+        x2 = x2.contiguous()
+    weight = _plain(weight)
+    if weight.dtype != x.dtype or weight.stride(-1) != 1 or (weight.stride(0) % 8) != 0:
+        weight = weight.to(x.dtype).contiguous()
+    M = x2.shape[0]
+    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    bias_ptr, bias_code = None, 0
+    if bias is not None:
+        bias = _plain(bias).contiguous()
+        bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ggufb200_gemm(weight.data_ptr(), N, K, weight.stride(0), x2.data_ptr(), M, x2.stride(0), dtype_code(x.dtype),
+                                      bias_ptr, bias_code, y.data_ptr(), N, torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, f"ggufb200_gemm(M={M}, N={N}, K={K})")
+    return y.reshape(*x.shape[:-1], N)
+
+
 class GGMLLayer(torch.nn.Module):
     """On-the-fly dequantising layer base (ops.py:93-225)."""
     comfy_cast_weights = True

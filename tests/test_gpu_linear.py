@@ -50,7 +50,7 @@ def test_linear_matches_reference_ops_golden(pkg, name, act, code, dt, golden_di
     xb = g["x"]
     x = torch.from_numpy(xb.view(np.float32) if code == 2 else xb.view(np.int16)).to(DEV)
     x = x.view(dt).reshape(M, K)
-    want = bits_to_f32(g["y"], code)
+    want = bits_to_f32(g["y"].reshape(-1), code)
     for rows in (M, 5, 1):                       # M=24 -> large-M route, 5 and 1 -> fused GEMV
         y = lin(x[:rows])
         assert type(y) is torch.Tensor and y.dtype == dt and tuple(y.shape) == (rows, N)
