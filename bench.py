@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning knob: dequant CTAs per SM (0 = library default)")
     ap.add_argument("--sweep-detail", action="store_true", help="also print per-(qtype,shape) GB/s lines to stderr")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -201,6 +202,8 @@ def main():
 
     dq, ops, rep = ge._sub("dequant"), ge._sub("ops"), ge._sub("replicas")
     lib = ge._sub("_lib").lib()        # raises if the CUDA extension is missing: no fallback
+    if args.ctas_per_sm:
+        lib.ggufb200_set_tuning(0, args.ctas_per_sm)
     rank, local_rank, world = rep.init()
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)

@@ -111,15 +111,15 @@ template <> struct Block<T_IQ4_NL> {  // dequant.py:243-256   layout of Q4_0, va
 
 // ---------------------------------------------------------------- K-quants, 256-element super-blocks
 // dequant.py:129-139: eight 6-bit (scale, min) pairs in 12 bytes s[0..11]
-template <int A> __device__ __forceinline__ void k_scale_min(const uint8_t *s, int j, int &sc, int &mn)
+// branch-free: the three little-endian words w0 = s[0..3], w1 = s[4..7], w2 = s[8..11]
+__device__ __forceinline__ void k_scale_min(const uint8_t *s, int j, int &sc, int &mn)
 {
-    if (j < 4) {
-        sc = s[j] & 63;
-        mn = s[j + 4] & 63;
-    } else {
-        sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4);
-        mn = (s[j + 4] >> 4) | ((s[j] >> 6) << 4);
-    }
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s);   // blk + 4 is 4-byte aligned for Q4_K / Q5_K
+    const int sh = 8 * (j & 3);
+    const uint32_t a = (w[0] >> sh) & 0xFFu, b = (w[1] >> sh) & 0xFFu, c = (w[2] >> sh) & 0xFFu;
+    const bool hi = j >= 4;
+    sc = hi ? (int)((c & 0x0Fu) | ((a >> 6) << 4)) : (int)(a & 63u);
+    mn = hi ? (int)((c >> 4) | ((b >> 6) << 4)) : (int)(b & 63u);
 }
 
 template <> struct Block<T_Q2_K> {  // dequant.py:221-238   [scales 16][qs 64][d][dmin]
@@ -166,7 +166,7 @@ template <> struct Block<T_Q4_K> {  // dequant.py:180-195   [d][dmin][scales 12]
     }
     static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
-        k_scale_min<4>(b + 4, e0 >> 5, sc, mn);
+        k_scale_min(b + 4, e0 >> 5, sc, mn);
     }
 };
 template <> struct Block<T_Q5_K> {  // dequant.py:159-178   [d][dmin][scales 12][qh 32][qs 128]
@@ -182,7 +182,7 @@ template <> struct Block<T_Q5_K> {  // dequant.py:159-178   [d][dmin][scales 12]
     }
     static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
-        k_scale_min<4>(b + 4, e0 >> 5, sc, mn);
+        k_scale_min(b + 4, e0 >> 5, sc, mn);
     }
 };
 template <> struct Block<T_Q6_K> {  // dequant.py:141-157   [ql 128][qh 64][scales i8 16][d]
@@ -224,42 +224,69 @@ template <> struct Block<T_IQ4_XS> {  // dequant.py:258-285   [d][scales_h u16][
 };
 
 // ---------------------------------------------------------------- float step shared by every consumer
-// N consecutive elements (N = 4 or 8, e0 % N == 0) of one block -> N/2 pairs in the math dtype,
-// op order and per-op rounding exactly as the reference (see oracle/gguf_oracle.c::float_step).
-template <class Q, int MATH, int N>
-__device__ __forceinline__ void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
+// The multiplier / offset pair (a, b) of the float step is constant over a GROUP of consecutive elements:
+//   KIND 0: a = d              KIND 1: a = d, b = m          (GROUP = the 32-element block)
+//   KIND 2: a = d*sc           KIND 3: a = d*sc, b = dmin*mn (GROUP = 32 for Q4_K/Q5_K/IQ4_XS, 16 for Q2_K/Q3_K/Q6_K)
+// Consumers that walk a whole group (standalone dequant, fused GEMM) compute it once per group.
+template <class Q> struct GroupOf {
+    static constexpr int value = (Q::BS == 32) ? 32 : ((Q::TS == 144 || Q::TS == 176 || Q::TS == 136) ? 32 : 16);
+};
+
+template <int MATH> struct GroupScale {
+    typename Math<MATH>::T2 a, b;
+};
+
+template <class Q, int MATH> __device__ __forceinline__ GroupScale<MATH> group_scale(const uint8_t *blk, int e0)
 {
     using M = Math<MATH>;
-    static_assert(N == 4 || N == 8, "run length");
+    GroupScale<MATH> g;
     typename M::T d = M::from_h(Q::d_bits(blk));
-    typename M::T2 a, b;
     if constexpr (Q::KIND == 0) {
-        a = M::bcast(d);
+        g.a = M::bcast(d);
+        g.b = g.a;
     } else if constexpr (Q::KIND == 1) {
-        a = M::bcast(d);
-        b = M::bcast(M::from_h(Q::d2_bits(blk)));
+        g.a = M::bcast(d);
+        g.b = M::bcast(M::from_h(Q::d2_bits(blk)));
     } else {
         int sc, mn;
         Q::scales(blk, e0, sc, mn);
-        a = M::bcast(M::mul(d, M::from_int(sc)));
-        if constexpr (Q::KIND == 3) b = M::bcast(M::mul(M::from_h(Q::d2_bits(blk)), M::from_int(mn)));
+        g.a = M::bcast(M::mul(d, M::from_int(sc)));
+        if constexpr (Q::KIND == 3) g.b = M::bcast(M::mul(M::from_h(Q::d2_bits(blk)), M::from_int(mn)));
+        else g.b = g.a;
     }
+    return g;
+}
+
+// N consecutive elements (N = 4 or 8, e0 % N == 0, all inside one group) -> N/2 pairs in the math dtype,
+// op order and per-op rounding exactly as the reference (see oracle/gguf_oracle.c::float_step).
+template <class Q, int MATH, int N>
+__device__ __forceinline__ void dequant_elems(const uint8_t *blk, int e0, const GroupScale<MATH> &g, typename Math<MATH>::T2 (&out)[N / 2])
+{
+    using M = Math<MATH>;
+    static_assert(N == 4 || N == 8, "run length");
 #pragma unroll
     for (int j = 0; j < N / 4; ++j) {
         typename M::T2 lo, hi;
         M::cvt4(Q::q4(blk, e0 + 4 * j), Q::BIAS, lo, hi);
-        lo = M::mul2(a, lo);
-        hi = M::mul2(a, hi);
+        lo = M::mul2(g.a, lo);
+        hi = M::mul2(g.a, hi);
         if constexpr (Q::KIND == 1) {
-            lo = M::add2(lo, b);
-            hi = M::add2(hi, b);
+            lo = M::add2(lo, g.b);
+            hi = M::add2(hi, g.b);
         } else if constexpr (Q::KIND == 3) {
-            lo = M::sub2(lo, b);
-            hi = M::sub2(hi, b);
+            lo = M::sub2(lo, g.b);
+            hi = M::sub2(hi, g.b);
         }
         out[2 * j] = lo;
         out[2 * j + 1] = hi;
     }
+}
+
+template <class Q, int MATH, int N>
+__device__ __forceinline__ void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
+{
+    const GroupScale<MATH> g = group_scale<Q, MATH>(blk, e0);
+    dequant_elems<Q, MATH, N>(blk, e0, g, out);
 }
 
 }  // namespace ggufb200

@@ -21,35 +21,52 @@ constexpr int kThreads = 256;
 
 int g_dequant_ctas_per_sm = 0;  // 0 = default; set through ggufb200_set_tuning(0, v)
 
+// bulk async copy shared -> global (TMA engine), tracked with bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One thread = one run of 32 consecutive elements (a whole 32-block, or one/two scale groups of a K-quant
+// super-block): the header is decoded once per 32 elements.  The 32 results (64 B fp16/bf16, 128 B fp32) go to a
+// linear output tile in shared memory in 16-byte chunks -- chunk order rotated per lane so the STS.128 are bank
+// conflict free -- and the finished tile leaves through ONE bulk async store (TMA engine), so the threads never
+// compute a global address and every HBM write is a full line.
 template <class Q, int MATH, int OUT, int STAGES, int TILE_ELEMS>
 __global__ void __launch_bounds__(kThreads) dequant_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst, long long n_blocks,
                                                            int bulk_ok)
 {
-    constexpr int EPT = 16 / OutT<OUT>::bytes;            // elements per 16-byte store: 8 or 4
+    constexpr int OB = OutT<OUT>::bytes;
+    constexpr int EPC = 16 / OB;                           // elements per 16-byte chunk: 8 or 4
+    constexpr int CH = 32 / EPC;                           // chunks per thread: 4 or 8
     constexpr int TILE_BLOCKS = TILE_ELEMS / Q::BS;
     constexpr int TILE_BYTES = TILE_BLOCKS * Q::TS;
-    constexpr int SLOT_BYTES = TILE_BYTES + 16;           // +16: tail over-read rounding
-    constexpr int ITERS = TILE_ELEMS / (kThreads * EPT);
+    constexpr int SLOT_BYTES = TILE_BYTES + 16;            // +16: tail over-read rounding
+    constexpr int OUT_BYTES = TILE_ELEMS * OB;
+    constexpr int GROUP = GroupOf<Q>::value;
     static_assert(TILE_BYTES % 16 == 0, "tile byte span must be a multiple of 16");
-    static_assert(TILE_ELEMS % (kThreads * EPT) == 0 && TILE_ELEMS % Q::BS == 0, "tile shape");
+    static_assert(TILE_ELEMS == kThreads * 32 && TILE_ELEMS % Q::BS == 0, "tile shape");
 
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);   // STAGES mbarriers
     uint8_t *slots = smem + 128;
+    uint8_t *outs = slots + STAGES * SLOT_BYTES;           // two output tiles
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     const long long total_bytes = n_blocks * (long long)Q::TS;
     const long long n_elems = n_blocks * (long long)Q::BS;
 
-    if (bulk_ok) {
-        if (tid == 0) {
+    if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
     }
+    __syncthreads();
 
     // bytes of tile t (the last tile may be short); bulk copies are rounded up to 16 B, which
     // stays inside the 16-byte granule that holds the last valid byte
@@ -70,10 +87,16 @@ __global__ void __launch_bounds__(kThreads) dequant_kernel(const uint8_t *__rest
         }
     }
 
+    // this thread's run inside any tile
+    const int blk_in_tile = (tid * 32) / Q::BS;
+    const int e0 = (tid * 32) % Q::BS;
+    const int rot = (CH == 4) ? (lane >> 1) : lane;
+
     int it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int slot = it % STAGES;
         const uint8_t *tile = slots + slot * SLOT_BYTES;
+        uint8_t *otile = outs + (it & 1) * OUT_BYTES;
         if (bulk_ok) {
             mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
         } else {
@@ -86,29 +109,46 @@ __global__ void __launch_bounds__(kThreads) dequant_kernel(const uint8_t *__rest
         }
 
         const long long elem_base = t * (long long)TILE_ELEMS;
+        const long long left = n_elems - elem_base;
+        const int tile_elems = left < TILE_ELEMS ? (int)left : TILE_ELEMS;   // a multiple of 32
+        if (tid * 32 < tile_elems) {
+            const uint8_t *blk = tile + blk_in_tile * Q::TS;
+            const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
+            GroupScale<MATH> g1 = g0;
+            if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
+            const uint32_t obase = smem_u32(otile) + tid * (32 * OB);
 #pragma unroll
-        for (int p = 0; p < ITERS; ++p) {
-            const int idx = (p * kThreads + tid) * EPT;     // element index inside the tile
-            if (elem_base + idx < n_elems) {
-                const int blk = idx / Q::BS;
-                const int e0 = idx % Q::BS;
-                typename Math<MATH>::T2 v[EPT / 2];
-                dequant_run<Q, MATH, EPT>(tile + blk * Q::TS, e0, v);
-                uint8_t *o = reinterpret_cast<uint8_t *>(dst) + (elem_base + idx) * (long long)OutT<OUT>::bytes;
+            for (int p = 0; p < CH; ++p) {
+                const int c = (p + rot) & (CH - 1);          // rotated chunk order: conflict-free STS.128
+                const int e = e0 + c * EPC;
+                const bool second = (GROUP == 16) && (c * EPC >= 16);
+                GroupScale<MATH> g;
+                g.a = second ? g1.a : g0.a;
+                g.b = second ? g1.b : g0.b;
+                typename Math<MATH>::T2 v[EPC / 2];
+                dequant_elems<Q, MATH, EPC>(blk, e, g, v);
                 if constexpr (OUT == kF32) {
                     float2 f0 = Math<MATH>::to_f32x2(v[0]), f1 = Math<MATH>::to_f32x2(v[1]);
-                    st_global_v4(o, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
+                    st_shared_v4(obase + c * 16, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
                 } else {
-                    st_global_v4(o, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]), pack16<OUT, MATH>(v[3]));
+                    st_shared_v4(obase + c * 16, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]),
+                                 pack16<OUT, MATH>(v[3]));
                 }
             }
         }
-        __syncthreads();  // every thread is done reading this slot
-        if (bulk_ok && tid == 0) {
-            long long tn = t + (long long)STAGES * gridDim.x;
-            if (tn < n_tiles) issue(tn, slot);
+        fence_proxy_async_smem();   // output tile written through the generic proxy, read by the TMA engine
+        __syncthreads();            // tile complete; every thread is also done reading the input slot
+        if (tid == 0) {
+            bulk_s2g(reinterpret_cast<uint8_t *>(dst) + elem_base * OB, otile, (uint32_t)(tile_elems * OB));
+            if (bulk_ok) {
+                long long tn = t + (long long)STAGES * gridDim.x;
+                if (tn < n_tiles) issue(tn, slot);
+            }
+            bulk_wait_read_le1();   // the other output buffer (stored one tile ago) has been read out
         }
+        __syncthreads();
     }
+    if (tid == 0) bulk_wait_all();
 }
 
 // BF16 "quantised" type (dequant.py:61-62): widen to fp32, then cast to the output dtype
@@ -183,11 +223,11 @@ static int sm_count()
 
 template <class Q, int MATH, int OUT> static int launch_dequant(const void *packed, long long n_blocks, void *out, cudaStream_t st)
 {
-    constexpr int STAGES = 4;
-    constexpr int TILE_ELEMS = 2048;
+    constexpr int STAGES = 3;
+    constexpr int TILE_ELEMS = kThreads * 32;
     constexpr int TILE_BLOCKS = TILE_ELEMS / Q::BS;
     constexpr int SLOT_BYTES = TILE_BLOCKS * Q::TS + 16;
-    constexpr int SMEM = 128 + STAGES * SLOT_BYTES;
+    constexpr int SMEM = 128 + STAGES * SLOT_BYTES + 2 * TILE_ELEMS * OutT<OUT>::bytes;
     auto kern = dequant_kernel<Q, MATH, OUT, STAGES, TILE_ELEMS>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -195,9 +235,10 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
         attr_done = true;
     }
     long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    int per_sm = g_dequant_ctas_per_sm > 0 ? g_dequant_ctas_per_sm : 6;
-    long long grid = (long long)sm_count() * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
+    int per_sm = g_dequant_ctas_per_sm > 0 ? g_dequant_ctas_per_sm : (OUT == kF32 ? 2 : 4);
+    long long cap = (long long)sm_count() * per_sm;
+    long long rounds = (n_tiles + cap - 1) / cap;            // every CTA gets the same number of tiles (+-1)
+    long long grid = (n_tiles + rounds - 1) / rounds;
     int bulk_ok = ((reinterpret_cast<uintptr_t>(packed) & 15) == 0) ? 1 : 0;
     kern<<<(unsigned)grid, kThreads, SMEM, st>>>(reinterpret_cast<const uint8_t *>(packed), out, n_blocks, bulk_ok);
     return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Per-shape timing of the quantised Linear at Flux.1 shapes: fused tcgen05 (ours) vs dequant+tcgen05 (ours) vs
+K1 dequant + cuBLAS vs cuBLAS on a pre-dequantised weight vs the reference's torch chain.  CUDA events, weights
+rotated through >L2 worth of distinct buffers.  Prints one line per (shape, route): ms, TFLOP/s."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import gguf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+import oracle  # noqa: E402
+from oracle import torch_chain  # noqa: E402
+
+SHAPES = [(3072, 3072), (9216, 3072), (12288, 3072), (3072, 12288), (18432, 3072), (21504, 3072), (3072, 15360)]
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qtype", default="Q4_K")
+    ap.add_argument("--M", type=int, nargs="+", default=[4608])
+    ap.add_argument("--shapes", type=int, nargs="*", default=None, help="indices into SHAPES")
+    ap.add_argument("--routes", nargs="*", default=["fused", "dq_mma", "k1_cublas", "cublas", "ref_chain"])
+    ap.add_argument("--copies", type=int, default=4)
+    args = ap.parse_args()
+    ops, dq, lib = ge._sub("ops"), ge._sub("dequant"), ge._sub("_lib")
+    dev = torch.device("cuda:0")
+    qt = gguf.GGMLQuantizationType[args.qtype]
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    shapes = SHAPES if not args.shapes else [SHAPES[i] for i in args.shapes]
+    for (N, K) in shapes:
+        ws = []
+        for c in range(args.copies):
+            chunk = min(N * K // bs, 1 << 15)
+            raw = torch.from_numpy(oracle.random_blocks(int(qt), chunk, seed=c, scale=0.02))
+            reps = (N * K // bs + chunk - 1) // chunk
+            packed = raw.repeat(reps, 1)[: N * K // bs].reshape(N, K // bs * ts).contiguous().to(dev)
+            ws.append(ops.GGMLTensor(packed, tensor_type=qt, tensor_shape=torch.Size((N, K))))
+        for M in args.M:
+            x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+            flops = 2.0 * M * N * K
+            state = {"i": 0}
+
+            def nxt():
+                state["i"] = (state["i"] + 1) % len(ws)
+                return ws[state["i"]]
+            dense = [dq.dequantize_tensor(w, torch.bfloat16) for w in ws[:2]] if "cublas" in args.routes else []
+            routes = {
+                "fused": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_MMA),
+                "dq_mma": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_DEQUANT_MMA),
+                "k1_cublas": lambda: torch.nn.functional.linear(x, dq.dequantize_tensor(nxt(), torch.bfloat16)),
+                "cublas": lambda: torch.nn.functional.linear(x, dense[state["i"] % 2]),
+                "ours_dense": lambda: ops.linear_dense(x, dense[state["i"] % 2]),
+                "ref_chain": lambda: torch_chain.linear(x, nxt().as_subclass(torch.Tensor), int(qt), (N, K)),
+            }
+            ref = None
+            for name in args.routes:
+                ms = timeit(routes[name])
+                y = routes[name]()
+                if ref is None:
+                    ref = torch.nn.functional.linear(x, dq.dequantize_tensor(ws[state["i"]], torch.bfloat16)).float()
+                err = float(((y.float() - ref).norm() / ref.norm()).item())
+                print(f"{args.qtype} N={N:6d} K={K:6d} M={M:5d} {name:10s} {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s  relerr={err:.2e}", flush=True)
+            del dense
+
+
+if __name__ == "__main__":
+    main()
