@@ -20,6 +20,7 @@ namespace ggufb200 {
 constexpr int kThreads = 256;
 
 int g_dequant_ctas_per_sm = 0;  // 0 = default; set through ggufb200_set_tuning(0, v)
+int g_dequant_pdl = 1;          // programmatic dependent launch of the dequant kernel; ggufb200_set_tuning(1, 0/1)
 
 // bulk async copy shared -> global (TMA engine), tracked with bulk async-groups
 __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
@@ -61,12 +62,16 @@ __global__ void __launch_bounds__(kThreads) dequant_kernel(const uint8_t *__rest
     const long long total_bytes = n_blocks * (long long)Q::TS;
     const long long n_elems = n_blocks * (long long)Q::BS;
 
+    // Programmatic dependent launch: let the next kernel in the stream be scheduled while this one drains, and
+    // do this kernel's own set-up before waiting for the previous kernel's memory to be complete and visible.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // bytes of tile t (the last tile may be short); bulk copies are rounded up to 16 B, which
     // stays inside the 16-byte granule that holds the last valid byte
@@ -229,19 +234,32 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
     constexpr int SLOT_BYTES = TILE_BLOCKS * Q::TS + 16;
     constexpr int SMEM = 128 + STAGES * SLOT_BYTES + 2 * TILE_ELEMS * OutT<OUT>::bytes;
     auto kern = dequant_kernel<Q, MATH, OUT, STAGES, TILE_ELEMS>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static int resident = 0;   // CTAs of this instantiation that fit on one SM
+    if (resident == 0) {
         if (SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        attr_done = true;
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, SMEM) != cudaSuccess || n < 1) n = 1;
+        resident = n > 4 ? 4 : n;
     }
     long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    int per_sm = g_dequant_ctas_per_sm > 0 ? g_dequant_ctas_per_sm : (OUT == kF32 ? 2 : 4);
+    int per_sm = g_dequant_ctas_per_sm > 0 ? g_dequant_ctas_per_sm : resident;
+    if (per_sm > resident) per_sm = resident;
     long long cap = (long long)sm_count() * per_sm;
     long long rounds = (n_tiles + cap - 1) / cap;            // every CTA gets the same number of tiles (+-1)
     long long grid = (n_tiles + rounds - 1) / rounds;
     int bulk_ok = ((reinterpret_cast<uintptr_t>(packed) & 15) == 0) ? 1 : 0;
-    kern<<<(unsigned)grid, kThreads, SMEM, st>>>(reinterpret_cast<const uint8_t *>(packed), out, n_blocks, bulk_ok);
-    return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_dequant_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const uint8_t *>(packed), out, (long long)n_blocks, bulk_ok);
+    return e == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 
 template <class Q, int MATH> static int dispatch_out(const void *packed, long long n_blocks, void *out, int out_dtype, cudaStream_t st)

@@ -128,7 +128,8 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
 int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx,
                   int act_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream);
 
-/* Tuning knob for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default). */
+/* Tuning knobs for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default),
+ * key 1 = programmatic dependent launch of the dequant kernel (default 1). */
 int ggufb200_set_tuning(int key, int value);
 
 #ifdef __cplusplus
