@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="tuning knob: disable programmatic dependent launch")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of replaying each step from a CUDA graph")
     ap.add_argument("--sweep-detail", action="store_true", help="also print per-(qtype,shape) GB/s lines to stderr")
+    ap.add_argument("--no-flux", action="store_true", help="skip the secondary metric (Flux.1-shape Q4_K denoise step A/B)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -373,6 +374,21 @@ def main():
                "what": "dequantize_tensor(GGMLTensor in pinned host memory) -> fp16 result copied back to pinned host memory, "
                        "for the [3072,3072] and [9216,3072] tensors of all 5 qtypes (10 tensors per step)"}
 
+    # ---------------- secondary BASELINE metric: Flux.1-dev-shape Q4_K_S 1024px denoise step, ours vs the reference's torch chain
+    flux = None
+    if not args.no_flux:
+        del tensors, t0
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_flux
+        try:
+            flux = bench_flux.run(steps=6, warmup=3, ref_steps=2 if rank == 0 else 0, device=f"cuda:{local_rank}")
+            flux["ms_per_step_max_over_ranks"] = rep.max_over_ranks(flux["ms_per_step"])
+            flux["replicas"] = world
+            flux["images_steps_per_s_all_replicas"] = world / (flux["ms_per_step_max_over_ranks"] * 1e-3)
+        except Exception as exc:   # the headline line must still be printed
+            flux = {"error": repr(exc)}
+
     cpu = cpu_baseline_run(args.cpu_budget) if rank == 0 else None
     rep.barrier()
     if rank == 0:
@@ -383,7 +399,7 @@ def main():
             "config": {"workload": WORKLOAD, "tensors_per_step": len(tensors), "elements_per_step": step_elems,
                        "algorithmic_bytes_per_step": step_bytes, "parallelism": f"{world} independent replica(s), no collective",
                        "l2": "inputs larger than L2: 1.05 GB of distinct packed tensors + 2.83 GB of distinct outputs per step vs 126 MB L2"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "flux_step": flux,
         }))
     rep.shutdown()
 

@@ -15,11 +15,31 @@ int gemm_fused_dispatch(int type, const void *W, long long N, long long K, const
                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                         int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
+                         int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm_fused_supported(int type);
 int gemv_max_m();
 }  // namespace ggufb200
 
 using namespace ggufb200;
+
+static int g_auto_fused = 0;     // large-M route picked by GGUFB200_ALGO_AUTO: 0 = dequant + tensor-core GEMM, 1 = fused; set_tuning(3, v)
+static int g_gemm_variant = 1;   // 0 = single-CTA UMMA (gemm.cu), 1 = CTA-pair UMMA cta_group::2 (gemm2.cu); ggufb200_set_tuning(2, v)
+
+static int fused_mma(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, int math,
+                     const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    return g_gemm_variant == 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st)
+                               : gemm_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st);
+}
+static int dense_mma(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act,
+                     const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    return g_gemm_variant == 1 ? gemm2_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st)
+                               : gemm_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
+}
 
 static bool type_geom(int t, int *bs, int *ts)
 {
@@ -81,7 +101,7 @@ int ggufb200_supported(int ggml_type, int op)
     case GGUFB200_OP_DEQUANT: return 1;
     case GGUFB200_OP_ROWS: return 1;
     case GGUFB200_OP_LINEAR: return 1;
-    case GGUFB200_OP_LINEAR_MMA: return gemm_fused_supported(ggml_type) ? 1 : 0;
+    case GGUFB200_OP_LINEAR_MMA: return 1;   // fused kernel, or dequant + tensor-core GEMM for types / shapes it does not cover
     }
     return 0;
 }
@@ -94,6 +114,14 @@ int ggufb200_set_tuning(int key, int value)
     }
     if (key == 1) {
         g_dequant_pdl = value ? 1 : 0;
+        return GGUFB200_OK;
+    }
+    if (key == 2) {
+        g_gemm_variant = value ? 1 : 0;
+        return GGUFB200_OK;
+    }
+    if (key == 3) {
+        g_auto_fused = value ? 1 : 0;
         return GGUFB200_OK;
     }
     return GGUFB200_E_UNSUPPORTED;
@@ -135,9 +163,10 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
 
 size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo)
 {
-    (void)M;
     if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0) return 0;
-    if (algo == GGUFB200_ALGO_DEQUANT_MMA) return (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
+    const size_t dense = (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
+    if (algo == GGUFB200_ALGO_DEQUANT_MMA) return dense;
+    if (algo == GGUFB200_ALGO_AUTO && M > gemv_max_m() && !(g_auto_fused && gemm_fused_supported(ggml_type))) return dense;
     return 0;
 }
 
@@ -156,8 +185,10 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     cudaStream_t st = (cudaStream_t)stream;
 
     if (algo == GGUFB200_ALGO_AUTO) {
+        const bool ws_ok = workspace && workspace_bytes >= (size_t)N * (size_t)K * 2;
+        const bool fused_ok = gemm_fused_supported(ggml_type) && math_dtype == kF16 && (K % 64) == 0;
         if (M <= gemv_max_m()) algo = GGUFB200_ALGO_GEMV;
-        else if (gemm_fused_supported(ggml_type)) algo = GGUFB200_ALGO_FUSED_MMA;
+        else if (fused_ok && (g_auto_fused || !ws_ok)) algo = GGUFB200_ALGO_FUSED_MMA;
         else algo = GGUFB200_ALGO_DEQUANT_MMA;
     }
     switch (algo) {
@@ -165,14 +196,14 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
         return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
     case GGUFB200_ALGO_FUSED_MMA:
         if (!gemm_fused_supported(ggml_type)) return GGUFB200_E_UNSUPPORTED;
-        return gemm_fused_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+        return fused_mma(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
     case GGUFB200_ALGO_DEQUANT_MMA: {
         size_t need = (size_t)N * (size_t)K * 2;
         if (!workspace || workspace_bytes < need) return GGUFB200_E_WORKSPACE;
         if (!aligned16(workspace)) return GGUFB200_E_ALIGN;
         int rc = dequant_dispatch(ggml_type, W_packed, N * (K / bs), workspace, act_dtype, math_dtype, st);
         if (rc != GGUFB200_OK) return rc;
-        return gemm_dense_dispatch(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
+        return dense_mma(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
     }
     }
     return GGUFB200_E_UNSUPPORTED;
@@ -187,7 +218,7 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
     if (M == 0) return GGUFB200_OK;
     if (!W || !X || !Y) return GGUFB200_E_NULL;
     if (!aligned16(W) || !aligned16(X) || !aligned16(Y) || (ldw % 8) || (ldx % 8) || (ldy % 8)) return GGUFB200_E_ALIGN;
-    return gemm_dense_dispatch(W, N, K, ldw, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, (cudaStream_t)stream);
+    return dense_mma(W, N, K, ldw, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,481 @@
+// gemm2.cu -- K2, CTA-pair version: tcgen05.mma.cta_group::2 (UMMA M=256 across two SMs, N=256).
+//
+//   Y[M,N] = X[M,K] * W[N,K]^T (+ bias)      fp16 / bf16 activations, fp32 accumulation in TMEM
+//
+// Why pairs: a single-CTA 128xN UMMA has to stream A (128x16) AND the whole B (Nx16) through one SM's shared
+// memory port for every instruction, and that port (128 B/clk) -- not the tensor pipe -- is what bounds the
+// single-CTA kernel in gemm.cu.  With cta_group::2 each SM of the pair holds 128 rows of A and only HALF of the
+// B tile (128 of 256 rows); the hardware reads both halves, so shared-memory traffic per flop halves.
+//
+// Cluster = 2 CTAs.  Pair tile = (256*ACCS) x 256 x 64:  ACCS accumulator sets of 256 TMEM columns each, so one
+// B tile (dequantised once, in FUSED mode) feeds 2*256*ACCS flops per element.
+//   CTA rank c holds   A rows  m0 + a*256 + c*128 .. +128   (a < ACCS)          -> 16 KB * ACCS per stage (TMA)
+//                      B rows  n0 + c*128 .. +128                                -> 16 KB per stage
+// Warp roles per CTA (512 threads): 0 TMA producer, 1 MMA issuer (leader CTA only), 2 TMEM alloc,
+// 4-7 epilogue acc 0, 8-15 dequant producers (FUSED), 8-11 epilogue acc 1.
+// Barriers live at identical offsets in both CTAs:
+//   full_a[s]  leader's copy collects the TMA bytes of BOTH CTAs (cp.async.bulk.tensor ... .cta_group::2, mbarrier
+//              operand mapped into the leader with mapa)
+//   full_b[s]  leader's copy collects one arrive per dequant thread of both CTAs (remote mbarrier.arrive)
+//   empty[s], tmem_full   signalled in both CTAs by tcgen05.commit ... .multicast::cluster (mask 0b11)
+#include <cuda.h>
+
+#include "blocks.cuh"
+
+namespace ggufb200 {
+
+constexpr int kG2Threads = 512;
+constexpr int kG2BK = 64;
+constexpr int kG2BN = 256;          // pair-level N (UMMA N); each CTA stages 128 rows of B
+constexpr int kG2DequantThreads = 256;
+
+template <int ACCS> struct Gemm2Cfg {
+    static constexpr int STAGES = ACCS == 2 ? 4 : 6;
+    static constexpr int A_BYTES = ACCS * 128 * kG2BK * 2;   // 16 KB per accumulator set
+    static constexpr int B_BYTES = 128 * kG2BK * 2;          // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+    static constexpr int TMEM_COLS = 256 * ACCS;
+};
+
+// ------------------------------------------------------------------ PTX helpers (cluster / cta_group::2 flavours)
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// arrive on the barrier at `cluster_addr` (a shared::cluster address obtained with mapa), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// TMA 2-D tile load whose completion bytes are credited to an mbarrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tm, uint32_t bar_cluster_addr, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar)   // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void g2_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g2_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void g2_tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void g2_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t g2_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor, D = f32, A/B K-major, UMMA M = 256 (pair), N = 256
+template <int ACT> __device__ __forceinline__ constexpr uint32_t g2_idesc()
+{
+    uint32_t fmt = ACT == kBF16 ? 1u : 0u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kG2BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+template <int ACT> __device__ __forceinline__ float g2_bias(const void *bias, int bias_dtype, long long n)
+{
+    float b;
+    if (bias_dtype == kF32) b = reinterpret_cast<const float *>(bias)[n];
+    else if (bias_dtype == kF16) b = __half2float(reinterpret_cast<const __half *>(bias)[n]);
+    else b = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(bias)[n]);
+    if constexpr (ACT == kBF16) return __bfloat162float(__float2bfloat16_rn(b));   // ops.py:205-207: bias is cast to x.dtype first
+    else return __half2float(__float2half_rn(b));
+}
+template <int ACT> __device__ __forceinline__ uint32_t g2_pack(float a, float b)
+{
+    if constexpr (ACT == kBF16) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&v);
+    } else {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t *>(&v);
+    }
+}
+
+struct Gemm2Params {
+    const uint8_t *W;      // FUSED: packed rows
+    long long row_bytes;
+    long long M, N, K;
+    const void *bias;
+    int bias_dtype;
+    uint8_t *Y;
+    long long ldy;
+    int tiles_m;
+};
+
+template <class Q, int MATH, int ACT, int ACCS>
+__global__ void __launch_bounds__(kG2Threads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p)
+{
+    using Cfg = Gemm2Cfg<ACCS>;
+    constexpr bool FUSED = !std::is_same<Q, void>::value;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t g2_smem_raw[];
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full_a = bars;
+    uint64_t *full_b = bars + STAGES;
+    uint64_t *empty = bars + 2 * STAGES;
+    uint64_t *tmem_full = bars + 3 * STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int tile_m = pair % p.tiles_m;
+    const int tile_n = pair / p.tiles_m;
+    const long long m0 = (long long)tile_m * (256 * ACCS);
+    const long long n0 = (long long)tile_n * kG2BN;
+    const int num_kb = (int)(p.K / kG2BK);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_a[s], 1);                         // the leader's arrive.expect_tx
+            mbar_init(&full_b[s], 2 * kG2DequantThreads);     // every dequant thread of both CTAs
+            mbar_init(&empty[s], 1);                          // multicast tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    g2_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // both CTAs' barriers are initialised before anything is signalled across the pair
+    g2_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (each CTA loads its own rows; bytes are credited to the leader's barrier)
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
+                uint8_t *a_dst = tiles + s * Cfg::STAGE_BYTES;
+                const uint32_t bar = mapa_u32(smem_u32(&full_a[s]), 0);
+                if (leader) mbar_arrive_expect_tx(&full_a[s], 2 * (FUSED ? Cfg::A_BYTES : Cfg::STAGE_BYTES));
+#pragma unroll
+                for (int a = 0; a < ACCS; ++a)
+                    tma_load_2d_pair(a_dst + a * (128 * 128), &tmA, bar, kb * kG2BK, (int)(m0 + a * 256 + rank * 128));
+                if constexpr (!FUSED) tma_load_2d_pair(a_dst + Cfg::A_BYTES, &tmB, bar, kb * kG2BK, (int)(n0 + rank * 128));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: leader CTA, one thread, drives the tensor cores of both SMs
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = g2_idesc<ACT>();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t par = (uint32_t)((kb / STAGES) & 1);
+                mbar_wait_cluster(&full_a[s], par);
+                if constexpr (FUSED) mbar_wait_cluster(&full_b[s], par);
+                g2_fence_after();
+                const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                for (int j = 0; j < kG2BK / 16; ++j) {
+                    const uint64_t db = g2_desc_sw128(b_addr + j * 32);
+                    const uint32_t acc = (kb > 0 || j > 0) ? 1u : 0u;
+#pragma unroll
+                    for (int a = 0; a < ACCS; ++a)
+                        umma_f16_pair(tmem_base + a * 256, g2_desc_sw128(a_addr + a * (128 * 128) + j * 32), db, idesc, acc);
+                }
+                umma_commit_pair(&empty[s]);
+            }
+            umma_commit_pair(tmem_full);
+        }
+    } else if (warp >= 8) {
+        // ===================== dequant producers (FUSED): this CTA's 128 rows of the B tile
+        if constexpr (FUSED) {
+            const int t = threadIdx.x - 256;
+            const int row = t >> 1;             // 0..127
+            const int half = t & 1;             // which 32-element half of the 64-wide k-block
+            const long long n = n0 + rank * 128 + row;
+            const bool valid = n < p.N;
+            const uint8_t *wrow = p.W + (valid ? n : 0) * p.row_bytes;
+            constexpr int GROUP = GroupOf<Q>::value;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
+                const uint32_t b_row = smem_u32(tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES) + row * 128;
+                if (valid) {
+                    const long long k = (long long)kb * kG2BK + half * 32;
+                    const uint8_t *blk = wrow + (k / Q::BS) * Q::TS;
+                    const int e0 = (int)(k % Q::BS);
+                    const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
+                    GroupScale<MATH> g1 = g0;
+                    if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        typename Math<MATH>::T2 v[4];
+                        dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
+                        const int chunk = half * 4 + c;
+                        st_shared_v4(b_row + ((chunk ^ (row & 7)) << 4), pack16<ACT, MATH>(v[0]), pack16<ACT, MATH>(v[1]),
+                                     pack16<ACT, MATH>(v[2]), pack16<ACT, MATH>(v[3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) st_shared_v4(b_row + (((half * 4 + c) ^ (row & 7)) << 4), 0, 0, 0, 0);
+                }
+                fence_proxy_async_all();
+                mbar_arrive_cluster(mapa_u32(smem_u32(&full_b[s]), 0));
+            }
+        }
+    }
+
+    // ===================== epilogue: every CTA drains its own 128 TMEM lanes of each accumulator set
+    if (warp >= 4 && warp < 4 + 4 * ACCS) {
+        const int acc = (warp - 4) >> 2;
+        const int quad = warp & 3;
+        mbar_wait_cluster(tmem_full, 0);
+        g2_fence_after();
+        const long long m = m0 + acc * 256 + rank * 128 + quad * 32 + lane;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
+        uint8_t *yrow = p.Y + (m * p.ldy + n0) * 2;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kG2BN; c0 += 32) {
+            uint32_t r[32];
+            g2_tmem_ld32(taddr0 + c0, r);
+            g2_tmem_ld_wait();
+            if (m < p.M) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const long long n = n0 + c0 + g * 8;
+                    if (n < p.N) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+                            if (p.bias) {
+                                v0 += g2_bias<ACT>(p.bias, p.bias_dtype, n + 2 * j);
+                                v1 += g2_bias<ACT>(p.bias, p.bias_dtype, n + 2 * j + 1);
+                            }
+                            o[j] = g2_pack<ACT>(v0, v1);
+                        }
+                        st_global_v4(yrow + (c0 + g * 8) * 2, o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    g2_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // no CTA leaves while its peer can still signal barriers in it / read its shared memory
+    if (warp == 2) {
+        g2_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*G2EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                               CUtensorMapFloatOOBfill);
+
+static G2EncodeFn g2_encode_fn()
+{
+    static G2EncodeFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<G2EncodeFn>(ptr);
+    }
+    return fn;
+}
+
+static bool g2_make_map(CUtensorMap *tm, const void *base, long long rows, long long K, long long ld, int act)
+{
+    G2EncodeFn fn = g2_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kG2BK, 128u};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapDataType dt = act == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    return fn(tm, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 512-row pair tiles halve the dequant work and the X traffic per flop; fall back to 256-row tiles when the last
+// wave of 512-row tiles would leave too many SM pairs idle
+static int g2_pick_accs(long long M, long long N)
+{
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long pairs = sms / 2;
+    auto eff = [&](int accs) {
+        long long tiles = ((M + 256 * accs - 1) / (256 * accs)) * ((N + kG2BN - 1) / kG2BN);
+        long long waves = (tiles + pairs - 1) / pairs;
+        return (double)tiles / (double)(waves * pairs);
+    };
+    if (M <= 256) return 1;
+    return eff(2) + 0.10 >= eff(1) ? 2 : 1;
+}
+
+template <class Q, int MATH, int ACT, int ACCS>
+static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2Params &p, cudaStream_t st)
+{
+    using Cfg = Gemm2Cfg<ACCS>;
+    auto kern = gemm2_kernel<Q, MATH, ACT, ACCS>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GGUFB200_E_CUDA;
+        attr = true;
+    }
+    Gemm2Params q = p;
+    q.tiles_m = (int)((p.M + 256 * ACCS - 1) / (256 * ACCS));
+    const long long tiles_n = (p.N + kG2BN - 1) / kG2BN;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * q.tiles_m * tiles_n));
+    cfg.blockDim = dim3(kG2Threads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, q) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <class Q, int ACT>
+static int g2_fused_act(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
+                        void *Y, long long ldy, cudaStream_t st)
+{
+    CUtensorMap tmA;
+    if (!g2_make_map(&tmA, X, M, K, ldx, ACT)) return GGUFB200_E_CUDA;
+    Gemm2Params p{};
+    p.W = reinterpret_cast<const uint8_t *>(W);
+    p.row_bytes = K / Q::BS * Q::TS;
+    p.M = M; p.N = N; p.K = K;
+    p.bias = bias; p.bias_dtype = bias_dtype;
+    p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
+    if (g2_pick_accs(M, N) == 2) return g2_launch<Q, kF16, ACT, 2>(tmA, tmA, p, st);
+    return g2_launch<Q, kF16, ACT, 1>(tmA, tmA, p, st);
+}
+
+int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    if (math_dtype != kF16 || K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
+#define GGUFB200_G2_CASE(T)                                                                                               \
+    case T:                                                                                                               \
+        return act_dtype == kBF16 ? g2_fused_act<Block<T>, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st)        \
+                                  : g2_fused_act<Block<T>, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
+    switch (type) {
+        GGUFB200_G2_CASE(T_Q4_0)
+        GGUFB200_G2_CASE(T_Q4_1)
+        GGUFB200_G2_CASE(T_Q5_0)
+        GGUFB200_G2_CASE(T_Q5_1)
+        GGUFB200_G2_CASE(T_Q8_0)
+        GGUFB200_G2_CASE(T_Q2_K)
+        GGUFB200_G2_CASE(T_Q3_K)
+        GGUFB200_G2_CASE(T_Q4_K)
+        GGUFB200_G2_CASE(T_Q5_K)
+        GGUFB200_G2_CASE(T_Q6_K)
+        GGUFB200_G2_CASE(T_IQ4_NL)
+        GGUFB200_G2_CASE(T_IQ4_XS)
+    }
+#undef GGUFB200_G2_CASE
+    return GGUFB200_E_UNSUPPORTED;
+}
+
+int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act_dtype,
+                         const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+{
+    if (K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
+    CUtensorMap tmA, tmB;
+    if (!g2_make_map(&tmA, X, M, K, ldx, act_dtype)) return GGUFB200_E_CUDA;
+    if (!g2_make_map(&tmB, W, N, K, ldw, act_dtype)) return GGUFB200_E_CUDA;
+    Gemm2Params p{};
+    p.M = M; p.N = N; p.K = K;
+    p.bias = bias; p.bias_dtype = bias_dtype;
+    p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
+    const int accs = g2_pick_accs(M, N);
+    if (act_dtype == kBF16) {
+        if (accs == 2) return g2_launch<void, kF16, kBF16, 2>(tmA, tmB, p, st);
+        return g2_launch<void, kF16, kBF16, 1>(tmA, tmB, p, st);
+    }
+    if (accs == 2) return g2_launch<void, kF16, kF16, 2>(tmA, tmB, p, st);
+    return g2_launch<void, kF16, kF16, 1>(tmA, tmB, p, st);
+}
+
+}  // namespace ggufb200

@@ -283,7 +283,12 @@ class GGMLOps(comfy_ops.manual_cast):
                 if b is not None and b.device != dev:
                     b = b.to(dev)
                 M = input.numel() // input.shape[-1]
-                if M <= GEMV_MAX_M or _lib.lib().ggufb200_supported(int(w.tensor_type), _lib.OP_LINEAR_MMA):
+                K = input.shape[-1]
+                if w.tensor_type == _Q.BF16 and M > GEMV_MAX_M:
+                    if input.dtype == torch.bfloat16 and K % 64 == 0:      # already dense: straight to the tensor-core GEMM
+                        dense = _plain(w).view(torch.bfloat16).view(w.tensor_shape[0], K)
+                        return linear_dense(input, dense, b)
+                elif M <= GEMV_MAX_M or (K % 64 == 0 and w.tensor_shape[0] % 8 == 0):
                     return linear_packed(input, w, b, self.dequant_dtype)
             weight, bias = self.cast_bias_weight(input)
             return torch.nn.functional.linear(input, weight, bias)

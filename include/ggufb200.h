@@ -129,7 +129,9 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
                   int act_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream);
 
 /* Tuning knobs for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default),
- * key 1 = programmatic dependent launch of the dequant kernel (default 1). */
+ * key 1 = programmatic dependent launch of the dequant kernel (default 1),
+ * key 2 = tensor-core GEMM variant: 1 = CTA-pair UMMA (cta_group::2, default), 0 = single-CTA UMMA,
+ * key 3 = large-M route chosen by GGUFB200_ALGO_AUTO: 0 = dequant + GEMM (default, needs the workspace), 1 = fused. */
 int ggufb200_set_tuning(int key, int value);
 
 #ifdef __cplusplus

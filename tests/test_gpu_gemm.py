@@ -15,6 +15,14 @@ DEV = "cuda:0"
 TOL = 1e-3
 
 
+@pytest.fixture(params=[1, 0], ids=["pair", "single"], autouse=True)
+def gemm_variant(request, pkg):
+    """Every test runs on both tensor-core kernels: CTA-pair (cta_group::2, default) and single-CTA."""
+    pkg.lib.lib().ggufb200_set_tuning(2, request.param)
+    yield request.param
+    pkg.lib.lib().ggufb200_set_tuning(2, 1)
+
+
 def _ref(x, W, bias):
     y = x.float() @ W.float().t()
     if bias is not None:

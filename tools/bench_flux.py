@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Flux.1-dev-shape Q4_K_S denoise step (1024x1024: 4096 img + 512 txt tokens, bf16, batch 1): this repo's GGMLOps vs the
+reference's torch-GPU chain (restated in oracle/torch_chain.py) on the same packed weights, same process, CUDA events.
+Prints one JSON object."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import __graft_entry__ as ge  # noqa: E402
+import flux_harness as fh  # noqa: E402
+
+
+def time_steps(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", fused=False,
+        block_qtype="Q4_K", batch=1):
+    ops_mod, lib = ge._sub("ops"), ge._sub("_lib")
+    lib.lib().ggufb200_set_tuning(3, 1 if fused else 0)
+    dev = torch.device(device)
+    qt = fh.Q[block_qtype]
+    with torch.no_grad():
+        ours = fh.FluxShapeDiT(ops_mod.GGMLOps, depth=depth, depth_single=depth_single)
+        ref = fh.FluxShapeDiT(fh.RefChainOps, depth=depth, depth_single=depth_single)
+        sd = fh.build_state_dict(ours, ops_mod.GGMLTensor, dev, block_qtype=qt)
+        fh.load_shared(ours, sd)
+        fh.load_shared(ref, sd)
+        ours.to(dev)
+        ref.to(dev)
+        inp = fh.make_inputs(dev, torch.bfloat16, batch=batch, img_tokens=img_tokens, txt_tokens=txt_tokens)
+        packed_bytes = sum(v.numel() * v.element_size() for k, v in sd.items() if k.endswith("weight"))
+        y_ours = ours(**inp)
+        y_ref = ref(**inp)
+        torch.cuda.synchronize()
+        rel = float(((y_ours.float() - y_ref.float()).norm() / y_ref.float().norm()).item())
+        finite = bool(torch.isfinite(y_ours).all().item())
+        ms_ours, min_ours = time_steps(lambda: ours(**inp), steps, warmup)
+        ms_ref, min_ref = time_steps(lambda: ref(**inp), ref_steps, 1) if ref_steps > 0 else (None, None)
+    flops = fh.linear_flops(ours, img_tokens, txt_tokens, batch)
+    return {
+        "workload": f"Flux.1-dev-shape DiT ({depth} double + {depth_single} single blocks), block Linears {block_qtype}, others BF16, "
+                    f"{img_tokens} img + {txt_tokens} txt tokens, bf16 activations, batch {batch}, random-init",
+        "ms_per_step": ms_ours, "min_ms": min_ours, "steps": steps,
+        "reference_chain_ms_per_step": ms_ref, "reference_chain_min_ms": min_ref,
+        "speedup_vs_reference_chain": (ms_ref / ms_ours) if ms_ref else None,
+        "linear_tflops_per_step": flops / 1e12, "linear_tflops_rate": flops / (ms_ours * 1e-3) / 1e12,
+        "packed_weight_gb": packed_bytes / 1e9, "output_rel_err_vs_reference_chain": rel, "output_finite": finite,
+        "large_m_route": "fused dequant+tcgen05" if fused else "dequant kernel + tcgen05 GEMM (CTA pair)",
+    }
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--depth", type=int, default=19)
+    ap.add_argument("--depth-single", type=int, default=38)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--ref-steps", type=int, default=3)
+    ap.add_argument("--txt", type=int, default=512)
+    ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--qtype", default="Q4_K")
+    a = ap.parse_args()
+    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, fused=a.fused, block_qtype=a.qtype)))

@@ -39,9 +39,11 @@ def main():
     ap.add_argument("--shapes", type=int, nargs="*", default=None, help="indices into SHAPES")
     ap.add_argument("--routes", nargs="*", default=["fused", "dq_mma", "k1_cublas", "cublas", "ref_chain"])
     ap.add_argument("--copies", type=int, default=4)
+    ap.add_argument("--variant", type=int, default=1, help="GEMM kernel: 1 = CTA pair, 0 = single CTA")
     args = ap.parse_args()
     ops, dq, lib = ge._sub("ops"), ge._sub("dequant"), ge._sub("_lib")
     dev = torch.device("cuda:0")
+    lib.lib().ggufb200_set_tuning(2, args.variant)
     qt = gguf.GGMLQuantizationType[args.qtype]
     bs, ts = gguf.GGML_QUANT_SIZES[qt]
     shapes = SHAPES if not args.shapes else [SHAPES[i] for i in args.shapes]
