@@ -374,6 +374,7 @@ def main():
                "what": "dequantize_tensor(GGMLTensor in pinned host memory) -> fp16 result copied back to pinned host memory, "
                        "for the [3072,3072] and [9216,3072] tensors of all 5 qtypes (10 tensors per step)"}
 
+    n_tensors = len(tensors)
     # ---------------- secondary BASELINE metric: Flux.1-dev-shape Q4_K_S 1024px denoise step, ours vs the reference's torch chain
     flux = None
     if not args.no_flux:
@@ -396,7 +397,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "tensors_per_step": len(tensors), "elements_per_step": step_elems,
+            "config": {"workload": WORKLOAD, "tensors_per_step": n_tensors, "elements_per_step": step_elems,
                        "algorithmic_bytes_per_step": step_bytes, "parallelism": f"{world} independent replica(s), no collective",
                        "l2": "inputs larger than L2: 1.05 GB of distinct packed tensors + 2.83 GB of distinct outputs per step vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "flux_step": flux,

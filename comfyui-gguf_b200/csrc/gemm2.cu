@@ -29,12 +29,23 @@ constexpr int kG2BK = 64;
 constexpr int kG2BN = 256;          // pair-level N (UMMA N); each CTA stages 128 rows of B
 constexpr int kG2DequantThreads = 256;
 
-template <int ACCS> struct Gemm2Cfg {
-    static constexpr int STAGES = ACCS == 2 ? 4 : 6;
+constexpr int kG2Span = 256;        // K elements covered by one packed-weight staging buffer (= 4 k-blocks)
+
+// SEG = bytes of one row's packed K-span; 0 = the format cannot be staged with a 2-D tensor map (SEG % 16 != 0)
+template <class Q> struct PackedSeg {
+    static constexpr int value = ((kG2Span / Q::BS) * Q::TS) % 16 == 0 ? (kG2Span / Q::BS) * Q::TS : 0;
+};
+template <> struct PackedSeg<void> {
+    static constexpr int value = 0;
+};
+
+template <int ACCS, int SEG = 0> struct Gemm2Cfg {
+    static constexpr int STAGES = SEG > 0 ? (ACCS == 2 ? 3 : 5) : (ACCS == 2 ? 4 : 6);
     static constexpr int A_BYTES = ACCS * 128 * kG2BK * 2;   // 16 KB per accumulator set
     static constexpr int B_BYTES = 128 * kG2BK * 2;          // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+    static constexpr int PACKED_BYTES = (128 * SEG + 127) & ~127;   // one staging buffer: 128 rows x SEG bytes
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * PACKED_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 256 * ACCS;
 };
 
@@ -174,22 +185,31 @@ struct Gemm2Params {
     int tiles_m;
 };
 
-template <class Q, int MATH, int ACT, int ACCS>
+// STAGED (FUSED only): the packed rows of the CTA's B half are staged through shared memory by a 2-D TMA over the raw
+// bytes ([N, row_bytes] uint8/uint16, box = SEG bytes x 128 rows) one 256-wide K-span (4 k-blocks) at a time, double
+// buffered, so the dequant warps read shared memory instead of paying an L2 round trip per 8 elements.  tmB is then the
+// tensor map of the packed weight.
+template <class Q, int MATH, int ACT, int ACCS, bool STAGED>
 __global__ void __launch_bounds__(kG2Threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p)
 {
-    using Cfg = Gemm2Cfg<ACCS>;
+    constexpr int SEG = STAGED ? PackedSeg<Q>::value : 0;
+    using Cfg = Gemm2Cfg<ACCS, SEG>;
     constexpr bool FUSED = !std::is_same<Q, void>::value;
     constexpr int STAGES = Cfg::STAGES;
+    static_assert(!STAGED || (FUSED && SEG > 0), "staging needs a fused format whose K-span is a multiple of 16 bytes");
 
     extern __shared__ uint8_t g2_smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + STAGES * Cfg::STAGE_BYTES);
+    uint8_t *packed = tiles + STAGES * Cfg::STAGE_BYTES;        // 2 x PACKED_BYTES (STAGED)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(packed + 2 * Cfg::PACKED_BYTES);
     uint64_t *full_a = bars;
     uint64_t *full_b = bars + STAGES;
     uint64_t *empty = bars + 2 * STAGES;
     uint64_t *tmem_full = bars + 3 * STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 1);
+    uint64_t *full_p = bars + 3 * STAGES + 1;                   // [2] packed buffer landed
+    uint64_t *empty_p = bars + 3 * STAGES + 3;                  // [2] packed buffer consumed by all dequant threads
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -209,6 +229,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(&empty[s], 1);                          // multicast tcgen05.commit
         }
         mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full_p[i], 1);
+            mbar_init(&empty_p[i], kG2DequantThreads);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
@@ -222,6 +246,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ===================== TMA producer (each CTA loads its own rows; bytes are credited to the leader's barrier)
         if (lane == 0) {
             for (int kb = 0; kb < num_kb; ++kb) {
+                if constexpr (STAGED) {
+                    if ((kb & 3) == 0) {   // next 256-wide K-span of this CTA's 128 packed rows
+                        const int span = kb >> 2, pb = span & 1;
+                        mbar_wait(&empty_p[pb], (uint32_t)(((span >> 1) & 1) ^ 1));
+                        mbar_arrive_expect_tx(&full_p[pb], 128 * SEG);
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                                smem_u32(packed + pb * Cfg::PACKED_BYTES)),
+                            "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_p[pb])), "r"(span * (SEG > 256 ? SEG / 2 : SEG)),
+                            "r"((int)(n0 + rank * 128))
+                            : "memory");
+                    }
+                }
                 const int s = kb % STAGES;
                 mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
                 uint8_t *a_dst = tiles + s * Cfg::STAGE_BYTES;
@@ -269,11 +306,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             constexpr int GROUP = GroupOf<Q>::value;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
+                if constexpr (STAGED) {
+                    if ((kb & 3) == 0) mbar_wait(&full_p[(kb >> 2) & 1], (uint32_t)((kb >> 3) & 1));
+                }
                 mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
                 const uint32_t b_row = smem_u32(tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES) + row * 128;
-                if (valid) {
+                if (valid || STAGED) {   // STAGED: rows past N were zero-filled by the TMA and dequantise to 0
                     const long long k = (long long)kb * kG2BK + half * 32;
-                    const uint8_t *blk = wrow + (k / Q::BS) * Q::TS;
+                    const int kin = STAGED ? (int)(k & (kG2Span - 1)) : 0;   // position inside the staged span
+                    const uint8_t *blk = STAGED ? packed + ((kb >> 2) & 1) * Cfg::PACKED_BYTES + row * SEG + (kin / Q::BS) * Q::TS
+                                                : wrow + (k / Q::BS) * Q::TS;
                     const int e0 = (int)(k % Q::BS);
                     const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
                     GroupScale<MATH> g1 = g0;
@@ -292,6 +334,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 fence_proxy_async_all();
                 mbar_arrive_cluster(mapa_u32(smem_u32(&full_b[s]), 0));
+                if constexpr (STAGED) {
+                    if ((kb & 3) == 3) mbar_arrive(&empty_p[(kb >> 2) & 1]);   // done with this packed buffer
+                }
             }
         }
     }
@@ -371,6 +416,8 @@ static bool g2_make_map(CUtensorMap *tm, const void *base, long long rows, long 
               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int g_fused_staged = 1;   // ggufb200_set_tuning(4, v): stage packed rows through shared memory in the fused kernel
+
 // 512-row pair tiles halve the dequant work and the X traffic per flop; fall back to 256-row tiles when the last
 // wave of 512-row tiles would leave too many SM pairs idle
 static int g2_pick_accs(long long M, long long N)
@@ -388,11 +435,11 @@ static int g2_pick_accs(long long M, long long N)
     return eff(2) + 0.10 >= eff(1) ? 2 : 1;
 }
 
-template <class Q, int MATH, int ACT, int ACCS>
+template <class Q, int MATH, int ACT, int ACCS, bool STAGED = false>
 static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2Params &p, cudaStream_t st)
 {
-    using Cfg = Gemm2Cfg<ACCS>;
-    auto kern = gemm2_kernel<Q, MATH, ACT, ACCS>;
+    using Cfg = Gemm2Cfg<ACCS, STAGED ? PackedSeg<Q>::value : 0>;
+    auto kern = gemm2_kernel<Q, MATH, ACT, ACCS, STAGED>;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GGUFB200_E_CUDA;
@@ -428,7 +475,28 @@ static int g2_fused_act(const void *W, long long N, long long K, const void *X, 
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_dtype = bias_dtype;
     p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
-    if (g2_pick_accs(M, N) == 2) return g2_launch<Q, kF16, ACT, 2>(tmA, tmA, p, st);
+    const int accs = g2_pick_accs(M, N);
+    constexpr int SEG = PackedSeg<Q>::value;
+    if constexpr (SEG > 0) {
+        // stage the packed rows through shared memory when a 2-D tensor map over the raw bytes is legal
+        if (g_fused_staged && K % kG2Span == 0 && p.row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+            G2EncodeFn fn = g2_encode_fn();
+            if (!fn) return GGUFB200_E_CUDA;
+            CUtensorMap tmW;
+            const bool wide = SEG > 256;     // inner box extent is limited to 256 elements: use 2-byte elements
+            cuuint64_t dims[2] = {(cuuint64_t)(wide ? p.row_bytes / 2 : p.row_bytes), (cuuint64_t)N};
+            cuuint64_t strides[1] = {(cuuint64_t)p.row_bytes};
+            cuuint32_t box[2] = {(cuuint32_t)(wide ? SEG / 2 : SEG), 128u};
+            cuuint32_t estr[2] = {1, 1};
+            if (fn(&tmW, wide ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(W), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return GGUFB200_E_CUDA;
+            if (accs == 2) return g2_launch<Q, kF16, ACT, 2, true>(tmA, tmW, p, st);
+            return g2_launch<Q, kF16, ACT, 1, true>(tmA, tmW, p, st);
+        }
+    }
+    if (accs == 2) return g2_launch<Q, kF16, ACT, 2>(tmA, tmA, p, st);
     return g2_launch<Q, kF16, ACT, 1>(tmA, tmA, p, st);
 }
 

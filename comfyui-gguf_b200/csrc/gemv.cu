@@ -49,22 +49,32 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const uint8_t *__res
 #pragma unroll
         for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
 
-        for (long long k = lane * 8; k < K; k += 256) {
-            typename Math<MATH>::T2 v[4];
-            dequant_run<Q, MATH, 8>(wrow + (k / Q::BS) * Q::TS, (int)(k % Q::BS), v);
-            float2 w[4];
+        // one lane = runs of 32 consecutive k: the block header / sub-block scales are decoded once per run
+        constexpr int GROUP = GroupOf<Q>::value;
+        for (long long k = lane * 32; k < K; k += 1024) {
+            const uint8_t *blk = wrow + (k / Q::BS) * Q::TS;
+            const int e0 = (int)(k % Q::BS);
+            const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
+            GroupScale<MATH> g1 = g0;
+            if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = act_bits_to_f32x2<ACT>(pack16<ACT, MATH>(v[j]));
+            for (int c = 0; c < 4; ++c) {
+                typename Math<MATH>::T2 v[4];
+                dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
+                float2 w[4];
 #pragma unroll
-            for (int m = 0; m < MM; ++m) {
-                if (m < M) {
-                    const uint4 xv = *reinterpret_cast<const uint4 *>(X + ((long long)m * ldx + k) * 2);
-                    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+                for (int j = 0; j < 4; ++j) w[j] = act_bits_to_f32x2<ACT>(pack16<ACT, MATH>(v[j]));
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float2 xf = act_bits_to_f32x2<ACT>(xs[j]);
-                        acc[m] = fmaf(w[j].x, xf.x, acc[m]);
-                        acc[m] = fmaf(w[j].y, xf.y, acc[m]);
+                for (int m = 0; m < MM; ++m) {
+                    if (m < M) {
+                        const uint4 xv = *reinterpret_cast<const uint4 *>(X + ((long long)m * ldx + k + c * 8) * 2);
+                        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 xf = act_bits_to_f32x2<ACT>(xs[j]);
+                            acc[m] = fmaf(w[j].x, xf.x, acc[m]);
+                            acc[m] = fmaf(w[j].y, xf.y, acc[m]);
+                        }
                     }
                 }
             }

@@ -15,12 +15,16 @@ DEV = "cuda:0"
 TOL = 1e-3
 
 
-@pytest.fixture(params=[1, 0], ids=["pair", "single"], autouse=True)
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["pair-staged", "pair", "single"], autouse=True)
 def gemm_variant(request, pkg):
-    """Every test runs on both tensor-core kernels: CTA-pair (cta_group::2, default) and single-CTA."""
-    pkg.lib.lib().ggufb200_set_tuning(2, request.param)
+    """Every test runs on the CTA-pair kernel (cta_group::2, default) with and without TMA-staged packed tiles in the
+    fused producer, and on the single-CTA kernel."""
+    variant, staged = request.param
+    pkg.lib.lib().ggufb200_set_tuning(2, variant)
+    pkg.lib.lib().ggufb200_set_tuning(4, staged)
     yield request.param
     pkg.lib.lib().ggufb200_set_tuning(2, 1)
+    pkg.lib.lib().ggufb200_set_tuning(4, 1)
 
 
 def _ref(x, W, bias):

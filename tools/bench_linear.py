@@ -63,9 +63,10 @@ def main():
             def nxt():
                 state["i"] = (state["i"] + 1) % len(ws)
                 return ws[state["i"]]
-            dense = [dq.dequantize_tensor(w, torch.bfloat16) for w in ws[:2]] if "cublas" in args.routes else []
+            dense = [dq.dequantize_tensor(w, torch.bfloat16) for w in ws[:2]] if ("cublas" in args.routes or "ours_dense" in args.routes) else []
             routes = {
                 "fused": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_MMA),
+                "auto": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_AUTO),
                 "dq_mma": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_DEQUANT_MMA),
                 "k1_cublas": lambda: torch.nn.functional.linear(x, dq.dequantize_tensor(nxt(), torch.bfloat16)),
                 "cublas": lambda: torch.nn.functional.linear(x, dense[state["i"] % 2]),
