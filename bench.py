@@ -108,8 +108,8 @@ def cpu_baseline_run(budget_s=12.0, threads=None):
     the [3072,3072] member of every qtype in the sweep, fp16 math, fp16 out; repeated until ~budget_s."""
     import gguf
     import oracle
-    if threads:
-        oracle.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every host core explicitly
+    oracle.set_num_threads(threads or os.cpu_count() or 1)
     cores = oracle.num_threads()
     N, K = 3072, 3072
     tensors = []
@@ -149,6 +149,7 @@ def run_reference(args):
         return
     import oracle
     import gguf
+    oracle.set_num_threads(os.cpu_count() or 1)   # torchrun sets OMP_NUM_THREADS=1 for its workers
     N, K = 3072, 3072
     tensors = []
     for q in QTYPES:
@@ -337,7 +338,12 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "dequant_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file))
+            tf = json.load(open(traffic_file))
+            pl = tf["per_launch"]
+            roofline["traffic"] = sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in pl) / len(pl)
+            roofline["traffic_algorithmic_same_launches"] = sum(x["algorithmic_read_bytes"] + x["algorithmic_write_bytes"] for x in pl) / len(pl)
+            roofline["traffic_unit"] = "bytes per launch (mean over the 7 Q4_K launches of one ncu --set full capture)"
+            roofline["traffic_note"] = tf["note"]
         except Exception:
             pass
 
