@@ -342,38 +342,59 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 
     // ===================== epilogue: every CTA drains its own 128 TMEM lanes of each accumulator set
-    if (warp >= 4 && warp < 4 + 4 * ACCS) {
-        const int acc = (warp - 4) >> 2;
+    // TMEM gives each lane one ROW (32 fp32 columns per tcgen05.ld), but a row-per-lane global store would touch 32
+    // different lines with 16 bytes each.  So every warp transposes through a private 32 x 80-byte staging tile in the
+    // (now idle) pipeline shared memory: phase 1 lane = row writes 64 B; phase 2 four lanes cover one row's 64 B, i.e.
+    // each st.global.v4 instruction writes eight fully covered 64-byte segments.
+    // All 16 warps take part once their main-loop role is finished: warp w may only touch TMEM lanes 32*(w%4)..+32, so
+    // the 16 warps split into 4 lane quadrants x 4 slots; a slot = (accumulator set, column range).
+    __syncwarp();
+    {
         const int quad = warp & 3;
+        const int slot = warp >> 2;                                  // 0..3
+        const int acc = ACCS == 2 ? (slot & 1) : 0;
+        constexpr int COLS = ACCS == 2 ? kG2BN / 2 : kG2BN / 4;      // columns per slot
+        const int col_begin = (ACCS == 2 ? (slot >> 1) : slot) * COLS;
         mbar_wait_cluster(tmem_full, 0);
         g2_fence_after();
-        const long long m = m0 + acc * 256 + rank * 128 + quad * 32 + lane;
+        const long long m_base = m0 + acc * 256 + rank * 128 + quad * 32;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
-        uint8_t *yrow = p.Y + (m * p.ldy + n0) * 2;
+        constexpr int PITCH = 80;                                   // 64 B of payload + 16 B pad: conflict-free 16-byte accesses
+        const uint32_t stage = smem_u32(tiles) + (uint32_t)warp * (32 * PITCH);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kG2BN; c0 += 32) {
+        for (int c0 = col_begin; c0 < col_begin + COLS; c0 += 32) {
             uint32_t r[32];
             g2_tmem_ld32(taddr0 + c0, r);
             g2_tmem_ld_wait();
-            if (m < p.M) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const long long n = n0 + c0 + g * 8;
-                    if (n < p.N) {
-                        uint32_t o[4];
+            for (int g = 0; g < 4; ++g) {
+                uint32_t o[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
-                            if (p.bias) {
-                                v0 += g2_bias<ACT>(p.bias, p.bias_dtype, n + 2 * j);
-                                v1 += g2_bias<ACT>(p.bias, p.bias_dtype, n + 2 * j + 1);
-                            }
-                            o[j] = g2_pack<ACT>(v0, v1);
+                for (int j = 0; j < 4; ++j) {
+                    float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+                    if (p.bias) {
+                        const long long n = n0 + c0 + g * 8 + 2 * j;
+                        if (n < p.N) {   // N % 8 == 0: the pair (n, n+1) is inside or outside together
+                            v0 += g2_bias<ACT>(p.bias, p.bias_dtype, n);
+                            v1 += g2_bias<ACT>(p.bias, p.bias_dtype, n + 1);
                         }
-                        st_global_v4(yrow + (c0 + g * 8) * 2, o[0], o[1], o[2], o[3]);
                     }
+                    o[j] = g2_pack<ACT>(v0, v1);
                 }
+                st_shared_v4(stage + lane * PITCH + g * 16, o[0], o[1], o[2], o[3]);
             }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int chunk = lane + 32 * q;          // 128 chunks of 16 B = 32 rows x 4
+                const int row = chunk >> 2, part = chunk & 3;
+                uint32_t a, b, c, d;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(stage + row * PITCH + part * 16));
+                const long long m = m_base + row;
+                const long long n = n0 + c0 + part * 8;
+                if (m < p.M && n < p.N) st_global_v4(p.Y + (m * p.ldy + n) * 2, a, b, c, d);
+            }
+            __syncwarp();
         }
     }
 
