@@ -20,6 +20,8 @@ int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, cons
                          int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                          int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
+                         int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm_fused_supported(int type);
 int gemv_max_m();
 }  // namespace ggufb200
@@ -27,17 +29,19 @@ int gemv_max_m();
 using namespace ggufb200;
 
 static int g_auto_fused = 0;     // large-M route picked by GGUFB200_ALGO_AUTO: 0 = dequant + tensor-core GEMM, 1 = fused; set_tuning(3, v)
-static int g_gemm_variant = 1;   // 0 = single-CTA UMMA (gemm.cu), 1 = CTA-pair UMMA cta_group::2 (gemm2.cu); ggufb200_set_tuning(2, v)
+// 0 = single-CTA UMMA (gemm.cu), 1 = CTA-pair UMMA cta_group::2 (gemm2.cu), 2 = 1 + persistent double-buffered dense GEMM (gemm3.cu)
+static int g_gemm_variant = 2;   // ggufb200_set_tuning(2, v)
 
 static int fused_mma(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, int math,
                      const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
-    return g_gemm_variant == 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st)
+    return g_gemm_variant >= 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st)
                                : gemm_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st);
 }
 static int dense_mma(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act,
                      const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
+    if (g_gemm_variant == 2) return gemm3_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
     return g_gemm_variant == 1 ? gemm2_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st)
                                : gemm_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
 }
@@ -118,7 +122,7 @@ int ggufb200_set_tuning(int key, int value)
         return GGUFB200_OK;
     }
     if (key == 2) {
-        g_gemm_variant = value ? 1 : 0;
+        g_gemm_variant = value < 0 ? 0 : (value > 2 ? 2 : value);
         return GGUFB200_OK;
     }
     if (key == 3) {

@@ -130,7 +130,8 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
 
 /* Tuning knobs for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default),
  * key 1 = programmatic dependent launch of the dequant kernel (default 1),
- * key 2 = tensor-core GEMM variant: 1 = CTA-pair UMMA (cta_group::2, default), 0 = single-CTA UMMA,
+ * key 2 = tensor-core GEMM variant: 2 = CTA-pair UMMA + persistent double-buffered dense GEMM (default),
+ *         1 = CTA-pair UMMA (cta_group::2), 0 = single-CTA UMMA,
  * key 3 = large-M route chosen by GGUFB200_ALGO_AUTO: 0 = dequant + GEMM (default, needs the workspace), 1 = fused,
  * key 4 = fused kernel stages the packed rows through shared memory with TMA when legal (default 1). */
 int ggufb200_set_tuning(int key, int value);

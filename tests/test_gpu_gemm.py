@@ -15,7 +15,7 @@ DEV = "cuda:0"
 TOL = 1e-3
 
 
-@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["pair-staged", "pair", "single"], autouse=True)
+@pytest.fixture(params=[(2, 1), (1, 1), (1, 0), (0, 0)], ids=["persistent+pair-staged", "pair-staged", "pair", "single"], autouse=True)
 def gemm_variant(request, pkg):
     """Every test runs on the CTA-pair kernel (cta_group::2, default) with and without TMA-staged packed tiles in the
     fused producer, and on the single-CTA kernel."""
@@ -23,7 +23,7 @@ def gemm_variant(request, pkg):
     pkg.lib.lib().ggufb200_set_tuning(2, variant)
     pkg.lib.lib().ggufb200_set_tuning(4, staged)
     yield request.param
-    pkg.lib.lib().ggufb200_set_tuning(2, 1)
+    pkg.lib.lib().ggufb200_set_tuning(2, 2)
     pkg.lib.lib().ggufb200_set_tuning(4, 1)
 
 

@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--shapes", type=int, nargs="*", default=None, help="indices into SHAPES")
     ap.add_argument("--routes", nargs="*", default=["fused", "dq_mma", "k1_cublas", "cublas", "ref_chain"])
     ap.add_argument("--copies", type=int, default=4)
-    ap.add_argument("--variant", type=int, default=1, help="GEMM kernel: 1 = CTA pair, 0 = single CTA")
+    ap.add_argument("--variant", type=int, default=2, help="GEMM kernel: 2 = persistent pair (dense) + pair (fused), 1 = CTA pair, 0 = single CTA")
     args = ap.parse_args()
     ops, dq, lib = ge._sub("ops"), ge._sub("dequant"), ge._sub("_lib")
     dev = torch.device("cuda:0")

@@ -27,7 +27,7 @@ def timeit(fn, iters=20, warm=3):
     return a.elapsed_time(b) / iters
 
 
-for variant in (1, 0):
+for variant in (2, 1):
     lib.lib().ggufb200_set_tuning(2, variant)
     for (M, N) in ((4608, 12288), (4736, 9472)):     # 2nd: 18.5x37 = exactly full waves of 512x256 pair tiles? (tiles=10*37=370=5*74)
         res = []
