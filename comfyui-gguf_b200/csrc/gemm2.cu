@@ -61,10 +61,11 @@ struct Gemm2Params {
 // buffered, so the dequant warps read shared memory instead of paying an L2 round trip per 8 elements.  tmB is then the
 // tensor map of the packed weight.
 template <class Q, int MATH, int ACT, int ACCS, bool STAGED>
-__global__ void __launch_bounds__(kG2Threads, 1)
+__global__ void __launch_bounds__(STAGED ? 768 : kG2Threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p)
 {
     constexpr int SEG = STAGED ? PackedSeg<Q>::value : 0;
+    constexpr int DQ = STAGED ? 512 : kG2DequantThreads;      // dequant producer threads: 16 warps when the packed rows sit in smem
     using Cfg = Gemm2Cfg<ACCS, SEG>;
     constexpr bool FUSED = !std::is_same<Q, void>::value;
     constexpr int STAGES = Cfg::STAGES;
@@ -80,7 +81,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t *tmem_full = bars + 3 * STAGES;
     uint64_t *full_p = bars + 3 * STAGES + 1;                   // [2] packed buffer landed
     uint64_t *empty_p = bars + 3 * STAGES + 3;                  // [2] packed buffer consumed by all dequant threads
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 5);
+    uint64_t *full_b2 = bars + 3 * STAGES + 5;                  // [STAGES] leader's copy: both CTAs' B halves are complete
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * STAGES + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -96,13 +98,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_a[s], 1);                         // the leader's arrive.expect_tx
-            mbar_init(&full_b[s], 2 * kG2DequantThreads);     // every dequant thread of both CTAs
+            mbar_init(&full_b[s], DQ / 32);                   // LOCAL: one arrive per dequant warp of this CTA
+            mbar_init(&full_b2[s], 2);                        // leader's copy: one relay arrive per CTA
             mbar_init(&empty[s], 1);                          // multicast tcgen05.commit
         }
         mbar_init(tmem_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&full_p[i], 1);
-            mbar_init(&empty_p[i], kG2DequantThreads);
+            mbar_init(&empty_p[i], DQ / 32);
         }
         fence_mbar_init();
     }
@@ -149,7 +152,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int s = kb % STAGES;
                 const uint32_t par = (uint32_t)((kb / STAGES) & 1);
                 mbar_wait_cluster(&full_a[s], par);
-                if constexpr (FUSED) mbar_wait_cluster(&full_b[s], par);
+                if constexpr (FUSED) mbar_wait_cluster(&full_b2[s], par);
                 g2_fence_after();
                 const uint32_t a_addr = smem_u32(tiles + s * Cfg::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -165,12 +168,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             umma_commit_pair(tmem_full);
         }
+    } else if (warp == 3) {
+        // ===================== relay (FUSED): when this CTA's half of the B tile is complete, tell the leader's MMA issuer
+        if constexpr (FUSED) {
+            if (lane == 0) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int s = kb % STAGES;
+                    mbar_wait(&full_b[s], (uint32_t)((kb / STAGES) & 1));
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&full_b2[s]), 0));
+                }
+            }
+        }
     } else if (warp >= 8) {
         // ===================== dequant producers (FUSED): this CTA's 128 rows of the B tile
         if constexpr (FUSED) {
+            constexpr int TPR = DQ / 128;       // threads per B row: 2 (32 elements each) or 4 (16 elements each)
+            constexpr int CPT = 8 / TPR;        // 16-byte chunks per thread and k-block
             const int t = threadIdx.x - 256;
-            const int row = t >> 1;             // 0..127
-            const int half = t & 1;             // which 32-element half of the 64-wide k-block
+            const int row = t / TPR;            // 0..127
+            const int half = t % TPR;           // which part of the 64-wide k-block
             const long long n = n0 + rank * 128 + row;
             const bool valid = n < p.N;
             const uint8_t *wrow = p.W + (valid ? n : 0) * p.row_bytes;
@@ -183,30 +199,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
                 const uint32_t b_row = smem_u32(tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES) + row * 128;
                 if (valid || STAGED) {   // STAGED: rows past N were zero-filled by the TMA and dequantise to 0
-                    const long long k = (long long)kb * kG2BK + half * 32;
+                    const long long k = (long long)kb * kG2BK + half * (CPT * 8);
                     const int kin = STAGED ? (int)(k & (kG2Span - 1)) : 0;   // position inside the staged span
                     const uint8_t *blk = STAGED ? packed + ((kb >> 2) & 1) * Cfg::PACKED_BYTES + row * SEG + (kin / Q::BS) * Q::TS
                                                 : wrow + (k / Q::BS) * Q::TS;
                     const int e0 = (int)(k % Q::BS);
                     const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
                     GroupScale<MATH> g1 = g0;
-                    if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
+                    if constexpr (GROUP == 16 && CPT == 4) g1 = group_scale<Q, MATH>(blk, e0 + 16);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < CPT; ++c) {
                         typename Math<MATH>::T2 v[4];
                         dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
-                        const int chunk = half * 4 + c;
+                        const int chunk = half * CPT + c;
                         st_shared_v4(b_row + ((chunk ^ (row & 7)) << 4), pack16<ACT, MATH>(v[0]), pack16<ACT, MATH>(v[1]),
                                      pack16<ACT, MATH>(v[2]), pack16<ACT, MATH>(v[3]));
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) st_shared_v4(b_row + (((half * 4 + c) ^ (row & 7)) << 4), 0, 0, 0, 0);
+                    for (int c = 0; c < CPT; ++c) st_shared_v4(b_row + (((half * CPT + c) ^ (row & 7)) << 4), 0, 0, 0, 0);
                 }
-                fence_proxy_async_all();
-                mbar_arrive_cluster(mapa_u32(smem_u32(&full_b[s]), 0));
-                if constexpr (STAGED) {
-                    if ((kb & 3) == 3) mbar_arrive(&empty_p[(kb >> 2) & 1]);   // done with this packed buffer
+                // every lane publishes its own generic-proxy writes to the async proxy, the warp converges, and ONE lane
+                // signals the CTA-local barrier (release is cumulative over what __syncwarp ordered before it).  The
+                // cluster-scope hand-off to the MMA issuer is done by the relay warp, off the dequant warps' critical path.
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&full_b[s]);
+                    if constexpr (STAGED) {
+                        if ((kb & 3) == 3) mbar_arrive(&empty_p[(kb >> 2) & 1]);   // done with this packed buffer
+                    }
                 }
             }
         }
@@ -220,7 +242,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // All 16 warps take part once their main-loop role is finished: warp w may only touch TMEM lanes 32*(w%4)..+32, so
     // the 16 warps split into 4 lane quadrants x 4 slots; a slot = (accumulator set, column range).
     __syncwarp();
-    {
+    if (warp < 16) {
         const int quad = warp & 3;
         const int slot = warp >> 2;                                  // 0..3
         const int acc = ACCS == 2 ? (slot & 1) : 0;
@@ -283,7 +305,7 @@ int g_fused_staged = 1;   // ggufb200_set_tuning(4, v): stage packed rows throug
 
 // 512-row pair tiles halve the dequant work and the X traffic per flop; fall back to 256-row tiles when the last
 // wave of 512-row tiles would leave too many SM pairs idle
-static int g2_pick_accs(long long M, long long N)
+static int g2_pick_accs(long long M, long long N, bool fused = false)
 {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -295,6 +317,9 @@ static int g2_pick_accs(long long M, long long N)
         return (double)tiles / (double)(waves * pairs);
     };
     if (M <= 256) return 1;
+    // fused mode is bound by the dequant producers, whose work per flop halves with 512-row tiles (measured 1.15 vs
+    // 0.62 PFLOP/s), so a partly empty last wave is the smaller evil there
+    if (fused) return eff(2) * 1.15 >= eff(1) * 0.62 ? 2 : 1;
     return eff(2) + 0.10 >= eff(1) ? 2 : 1;
 }
 
@@ -313,7 +338,7 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
     const long long tiles_n = (p.N + kG2BN - 1) / kG2BN;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * q.tiles_m * tiles_n));
-    cfg.blockDim = dim3(kG2Threads);
+    cfg.blockDim = dim3(STAGED ? 768 : kG2Threads);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -338,7 +363,7 @@ static int g2_fused_act(const void *W, long long N, long long K, const void *X, 
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_dtype = bias_dtype;
     p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
-    const int accs = g2_pick_accs(M, N);
+    const int accs = g2_pick_accs(M, N, true);
     constexpr int SEG = PackedSeg<Q>::value;
     if constexpr (SEG > 0) {
         // stage the packed rows through shared memory when a 2-D tensor map over the raw bytes is legal
