@@ -68,6 +68,10 @@ except ImportError:
         class Embedding(_CastOp, torch.nn.Embedding):
             comfy_cast_weights = cast
 
+            def reset_parameters(self):
+                self.bias = None     # comfy.ops gives Embedding a (None) bias so the cast helpers can treat all ops alike
+                return None
+
             def forward_comfy_cast_weights(self, input, out_dtype=None):
                 want = out_dtype
                 if self.weight.dtype in (torch.float16, torch.bfloat16):

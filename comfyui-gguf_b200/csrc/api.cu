@@ -197,7 +197,10 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
         const bool ws_ok = workspace && workspace_bytes >= (size_t)N * (size_t)K * 2;
         const bool fused_ok = gemm_fused_supported(ggml_type) && math_dtype == kF16 && (K % 64) == 0;
         if (M <= gemv_max_m()) algo = GGUFB200_ALGO_GEMV;
-        else if (fused_ok && (g_auto_fused || !ws_ok)) algo = GGUFB200_ALGO_FUSED_MMA;
+        // measured on B200 (profiles/): with M >= ~1k the dequant-once + dense GEMM route wins (1.27-1.41 vs 0.86-1.15
+        // PFLOP/s); for short activations against a wide weight the fused kernel wins because the standalone dequant is
+        // no longer amortised over many M tiles
+        else if (fused_ok && (g_auto_fused || !ws_ok || (M <= 1024 && N >= 8192))) algo = GGUFB200_ALGO_FUSED_MMA;
         else algo = GGUFB200_ALGO_DEQUANT_MMA;
     }
     switch (algo) {

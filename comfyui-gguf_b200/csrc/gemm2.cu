@@ -36,11 +36,13 @@ template <> struct PackedSeg<void> {
 };
 
 template <int ACCS, int SEG = 0> struct Gemm2Cfg {
-    static constexpr int STAGES = SEG > 0 ? (ACCS == 2 ? 3 : 5) : (ACCS == 2 ? 4 : 6);
     static constexpr int A_BYTES = ACCS * 128 * kG2BK * 2;   // 16 KB per accumulator set
     static constexpr int B_BYTES = 128 * kG2BK * 2;          // this CTA's half of the B tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int PACKED_BYTES = (128 * SEG + 127) & ~127;   // one staging buffer: 128 rows x SEG bytes
+    static constexpr int BUDGET = 227 * 1024 - 256 - 1024 - 2 * PACKED_BYTES;   // what is left of the 227 KB for the A/B ring
+    static constexpr int WANT = ACCS == 2 ? 4 : 6;
+    static constexpr int STAGES = BUDGET / STAGE_BYTES < WANT ? BUDGET / STAGE_BYTES : WANT;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * PACKED_BYTES + 256 + 1024;
     static constexpr int TMEM_COLS = 256 * ACCS;
 };

@@ -63,6 +63,21 @@ def test_fused_gemm_all_types(pkg, qt, dt):
     assert rel_fro(y.float().cpu().numpy(), _ref(x, W, b).float().cpu().numpy()) <= TOL
 
 
+@pytest.mark.parametrize("route", ["fused", "dequant+mma", "auto"])
+def test_sd35_shape_q8_0_unaligned_rows(pkg, route):
+    """SD3.5-large hidden size 2432: Q8_0 rows are 2584 bytes (not a multiple of 16), so no tensor map over the packed bytes
+    is legal; the fused kernel must take its direct-load producer and K1 its flat byte-stream tiling."""
+    M, N, K = 700, 7296, 2432
+    raw = oracle.random_blocks(int(Q.Q8_0), N * K // 32, seed=2, scale=0.02).reshape(N, K // 32 * 34)
+    w = pkg.ops.GGMLTensor(torch.from_numpy(raw).to(DEV), tensor_type=Q.Q8_0, tensor_shape=torch.Size((N, K)))
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, device=DEV) * 0.1
+    algo = {"fused": pkg.lib.ALGO_FUSED_MMA, "dequant+mma": pkg.lib.ALGO_DEQUANT_MMA, "auto": pkg.lib.ALGO_AUTO}[route]
+    y = pkg.ops.linear_packed(x, w, b, None, algo)
+    W = pkg.dequant.dequantize_tensor(w, torch.bfloat16)
+    assert rel_fro(y.float().cpu().numpy(), _ref(x, W, b).float().cpu().numpy()) <= TOL
+
+
 @pytest.mark.parametrize("M,N,K", [(4608, 3072, 3072), (512, 9216, 3072), (4096, 3072, 12288)])
 def test_fused_gemm_flux_shapes_q4k(pkg, M, N, K):
     """Full Flux.1 Linear sizes: the oracle is too slow here, so compare against the dense route on the same weight
