@@ -333,11 +333,29 @@ int ggor_dequant(int type, const uint8_t *packed, int64_t n_blocks, void *out, i
         /* `d.view(float16).to(dtype)`: the header is first cast to the math dtype */
         float d = rnd(math_dtype, h2f(dh));
         float d2 = rnd(math_dtype, h2f(d2h));
-        for (int e = 0; e < bs; ++e) {
+        /* the sub-block scale / min are constant over aligned runs of 16 elements for every format: the two
+         * products d*sc and dmin*mn (each rounded once, as in the reference) are computed once per run */
+        for (int e0 = 0; e0 < bs; e0 += 16) {
             int q, sc, mn;
-            unpack_elem(type, B, e, &q, &sc, &mn);
-            float v = float_step(type, math_dtype, d, d2, q, sc, mn);
-            store_out(out, b * (int64_t)bs + e, out_dtype, v);
+            unpack_elem(type, B, e0, &q, &sc, &mn);
+            const float dl = rnd(math_dtype, d * (float)sc);
+            const float ml = rnd(math_dtype, d2 * (float)mn);
+            for (int e = e0; e < e0 + 16 && e < bs; ++e) {
+                int s2, m2;
+                unpack_elem(type, B, e, &q, &s2, &m2);
+                float v;
+                switch (type) {
+                case GG_Q4_0: case GG_Q5_0: case GG_Q8_0: case GG_IQ4_NL:
+                    v = rnd(math_dtype, d * (float)q); break;
+                case GG_Q4_1: case GG_Q5_1:
+                    v = rnd(math_dtype, rnd(math_dtype, d * (float)q) + d2); break;
+                case GG_Q3_K: case GG_Q6_K: case GG_IQ4_XS:
+                    v = rnd(math_dtype, dl * (float)q); break;
+                default: /* Q2_K, Q4_K, Q5_K */
+                    v = rnd(math_dtype, rnd(math_dtype, dl * (float)q) - ml); break;
+                }
+                store_out(out, b * (int64_t)bs + e, out_dtype, v);
+            }
         }
     }
     return 0;

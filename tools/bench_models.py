@@ -82,7 +82,7 @@ def run_t5(steps=6, ref_steps=2, layers=24, tokens=512):
     dev = torch.device("cuda:0")
     with torch.no_grad():
         ours, ref = T5ShapeEncoder(ops_mod.GGMLOps, layers), T5ShapeEncoder(fh.RefChainOps, layers)
-        sd = build_sd(ours, ops_mod.GGMLTensor, dev, fh.Q.Q5_K, bias=False, scale=1.5e-5)   # keeps the residual stream O(1)
+        sd = build_sd(ours, ops_mod.GGMLTensor, dev, fh.Q.Q5_K, bias=False, scale=5e-5)   # keeps the residual stream finite
         gen = torch.Generator(device=dev).manual_seed(5)
         table = ops_mod.GGMLTensor(fh.random_packed(fh.Q.Q5_K, 32128, 4096, dev, gen, scale=1e-3), tensor_type=fh.Q.Q5_K, tensor_shape=torch.Size((32128, 4096)))
         ours.shared.weight = nn.Parameter(table, requires_grad=False)
