@@ -244,13 +244,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // All 16 warps take part once their main-loop role is finished: warp w may only touch TMEM lanes 32*(w%4)..+32, so
     // the 16 warps split into 4 lane quadrants x 4 slots; a slot = (accumulator set, column range).
     __syncwarp();
+    // Wait for the accumulators WITHOUT spinning: one lane of the (otherwise idle) TMEM-allocator warp polls the mbarrier
+    // with a sleep back-off, every other warp parks on a hardware named barrier.  (Sixteen warps polling
+    // mbarrier.try_wait.acquire.cluster -- each success/failure followed by an L1 invalidate -- were ~30 % of all issued
+    // instructions of the fused kernel and competed with the dequant warps for issue slots.)
+    if (warp == 2) {
+        if (lane == 0) {
+            while (!mbar_try_wait(tmem_full, 0)) __nanosleep(200);
+        }
+        __syncwarp();
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory");
     if (warp < 16) {
         const int quad = warp & 3;
         const int slot = warp >> 2;                                  // 0..3
         const int acc = ACCS == 2 ? (slot & 1) : 0;
         constexpr int COLS = ACCS == 2 ? kG2BN / 2 : kG2BN / 4;      // columns per slot
         const int col_begin = (ACCS == 2 ? (slot >> 1) : slot) * COLS;
-        mbar_wait_cluster(tmem_full, 0);
         g2_fence_after();
         const long long m_base = m0 + acc * 256 + rank * 128 + quad * 32;
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256);
