@@ -133,7 +133,8 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
  * key 2 = tensor-core GEMM variant: 2 = CTA-pair UMMA + persistent double-buffered dense GEMM (default),
  *         1 = CTA-pair UMMA (cta_group::2), 0 = single-CTA UMMA,
  * key 3 = large-M route chosen by GGUFB200_ALGO_AUTO: 0 = dequant + GEMM (default, needs the workspace), 1 = fused,
- * key 4 = fused kernel stages the packed rows through shared memory with TMA when legal (default 1). */
+ * key 4 = fused kernel stages the packed rows through shared memory with TMA when legal (default 1),
+ * key 5 = small-M kernel: 1 = mma.sync tile kernel (default), 0 = warp-per-row FMA kernel. */
 int ggufb200_set_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -17,6 +17,14 @@ DEV = "cuda:0"
 TOL = 1e-3
 
 
+@pytest.fixture(params=[1, 0], ids=["gemv-mma", "gemv-fma"], autouse=True)
+def gemv_variant(request, pkg):
+    """Small-M Linears run on both GEMV kernels: the mma.sync tile kernel (default) and the warp-per-row FMA kernel."""
+    pkg.lib.lib().ggufb200_set_tuning(5, request.param)
+    yield request.param
+    pkg.lib.lib().ggufb200_set_tuning(5, 1)
+
+
 def _weight(pkg, qt, N, K, seed=0, scale=0.02):
     bs, ts = gguf.GGML_QUANT_SIZES[qt]
     raw = oracle.random_blocks(int(qt), N * K // bs, seed=seed, scale=scale).reshape(N, K // bs * ts)
