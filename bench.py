@@ -76,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -268,6 +268,9 @@ def main():
     if not np.array_equal(got, want):
         raise RuntimeError("bench: dequant output differs from the oracle; refusing to time a wrong kernel")
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()     # 20 ms samples from the warm-up through the timed region and the per-launch rounds below
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -286,12 +289,9 @@ def main():
         step()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     # ---------------- timed region: K steps, barrier + sync on both sides, device time via CUDA events
     rep.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -300,7 +300,6 @@ def main():
     torch.cuda.synchronize()
     rep.barrier()
     local_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = rep.max_over_ranks(local_ms)
     total_bytes = rep.sum_over_ranks(float(step_bytes) * args.steps)
     value = total_bytes / (total_ms * 1e-3) / 1e9
@@ -321,6 +320,7 @@ def main():
     for evs_r in evs[1:]:
         per_launch += np.array([a.elapsed_time(b) for a, b in evs_r])
     per_launch /= ROUNDS
+    clocks = sampler.stop() if rank == 0 else None
     mean_bytes = step_bytes / len(tensors)
     iso_ms = float(per_launch.mean())
     isolated = mean_bytes / (iso_ms * 1e-3) / 1e9

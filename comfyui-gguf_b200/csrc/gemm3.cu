@@ -19,12 +19,19 @@
 namespace ggufb200 {
 
 constexpr int kG3Threads = 512;
-constexpr int kG3Stages = 5;
-constexpr int kG3StageBytes = 2 * 128 * kG2BK * 2;     // A 16 KB + B 16 KB per CTA
 constexpr int kG3EpiWarps = 8;
 constexpr int kG3Pitch = 80;                            // staging row pitch (64 B payload + 16 B pad)
 constexpr int kG3StageOut = kG3EpiWarps * 32 * kG3Pitch;
-constexpr int kG3Smem = kG3Stages * kG3StageBytes + kG3StageOut + 256 + 1024;
+
+// BN = pair-level tile width (UMMA N): 256 by default; 128 when the problem has too few 256-wide tiles to occupy the
+// 74 SM pairs (short activations such as the 512-token text stream / T5): twice as many tiles, same pipeline.
+template <int BN> struct Gemm3Cfg {
+    static constexpr int A_BYTES = 128 * kG2BK * 2;            // 16 KB
+    static constexpr int B_BYTES = (BN / 2) * kG2BK * 2;       // this CTA's half of the B tile: 16 or 8 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BN == 256 ? 5 : 7;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + kG3StageOut + 256 + 1024;
+};
 
 struct Gemm3Params {
     long long M, N, K;
@@ -35,10 +42,13 @@ struct Gemm3Params {
     int tiles_m, n_tiles;
 };
 
-template <int ACT>
+template <int ACT, int BN>
 __global__ void __launch_bounds__(kG3Threads, 1)
 gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm3Params p)
 {
+    using Cfg = Gemm3Cfg<BN>;
+    constexpr int kG3Stages = Cfg::STAGES;
+    constexpr int kG3StageBytes = Cfg::STAGE_BYTES;
     extern __shared__ uint8_t g3_smem_raw[];
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(g3_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_out = tiles + kG3Stages * kG3StageBytes;
@@ -81,7 +91,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int it = 0;
             for (int tile = pair; tile < p.n_tiles; tile += n_pairs) {
                 const int m0 = (tile % p.tiles_m) * 256 + (int)rank * 128;
-                const int n0 = (tile / p.tiles_m) * kG2BN + (int)rank * 128;
+                const int n0 = (tile / p.tiles_m) * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % kG3Stages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kG3Stages) & 1) ^ 1));
@@ -96,13 +106,13 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA, one thread)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = g2_idesc<ACT>();
+            constexpr uint32_t idesc = g2_idesc<ACT, BN>();
             int it = 0, ti = 0;
             for (int tile = pair; tile < p.n_tiles; tile += n_pairs, ++ti) {
                 const int ab = ti & 1;
                 mbar_wait_cluster(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 g2_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(ab * 256);
+                const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % kG3Stages;
                     mbar_wait_cluster(&full[s], (uint32_t)((it / kG3Stages) & 1));
@@ -120,7 +130,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp >= 4 && warp < 4 + kG3EpiWarps) {
         // ===================== epilogue: overlaps the next tile's main loop
         const int quad = warp & 3;
-        const int col_begin = ((warp - 4) >> 2) * 128;
+        const int col_begin = ((warp - 4) >> 2) * (BN / 2);
         const uint32_t stage = smem_u32(stage_out) + (uint32_t)(warp - 4) * (32 * kG3Pitch);
         const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
@@ -128,12 +138,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int tile = pair; tile < p.n_tiles; tile += n_pairs, ++ti) {
             const int ab = ti & 1;
             const long long m_base = (long long)(tile % p.tiles_m) * 256 + rank * 128 + quad * 32;
-            const long long n0 = (long long)(tile / p.tiles_m) * kG2BN;
+            const long long n0 = (long long)(tile / p.tiles_m) * BN;
             mbar_wait_cluster(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
             g2_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
 #pragma unroll 1
-            for (int c0 = col_begin; c0 < col_begin + 128; c0 += 32) {
+            for (int c0 = col_begin; c0 < col_begin + BN / 2; c0 += 32) {
                 uint32_t r[32];
                 g2_tmem_ld32(taddr0 + c0, r);
                 g2_tmem_ld_wait();
@@ -182,10 +192,11 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 }
 
-template <int ACT>
+template <int ACT, int BN>
 static int g3_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, Gemm3Params p, cudaStream_t st)
 {
-    auto kern = gemm3_kernel<ACT>;
+    constexpr int kG3Smem = Gemm3Cfg<BN>::SMEM;
+    auto kern = gemm3_kernel<ACT, BN>;
     static bool attr = false;
     static int sms = 148;
     if (!attr) {
@@ -196,7 +207,7 @@ static int g3_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, Gemm3Params
         attr = true;
     }
     p.tiles_m = (int)((p.M + 255) / 256);
-    p.n_tiles = p.tiles_m * (int)((p.N + kG2BN - 1) / kG2BN);
+    p.n_tiles = p.tiles_m * (int)((p.N + BN - 1) / BN);
     int pairs = sms / 2;
     if (pairs > p.n_tiles) pairs = p.n_tiles;
     cudaLaunchConfig_t cfg{};
@@ -218,14 +229,20 @@ int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw,
                          const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
     if (K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
+    const bool narrow = tiles256 <= sms / 4;       // far fewer 256-wide tiles than SM pairs: halve the tile width
     CUtensorMap tmA, tmB;
     if (!g2_make_map(&tmA, X, M, K, ldx, act_dtype)) return GGUFB200_E_CUDA;
-    if (!g2_make_map(&tmB, W, N, K, ldw, act_dtype)) return GGUFB200_E_CUDA;
+    if (!g2_make_map(&tmB, W, N, K, ldw, act_dtype, narrow ? 64 : 128)) return GGUFB200_E_CUDA;
     Gemm3Params p{};
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_dtype = bias_dtype;
     p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
-    return act_dtype == kBF16 ? g3_launch<kBF16>(tmA, tmB, p, st) : g3_launch<kF16>(tmA, tmB, p, st);
+    if (narrow) return act_dtype == kBF16 ? g3_launch<kBF16, 128>(tmA, tmB, p, st) : g3_launch<kF16, 128>(tmA, tmB, p, st);
+    return act_dtype == kBF16 ? g3_launch<kBF16, 256>(tmA, tmB, p, st) : g3_launch<kF16, 256>(tmA, tmB, p, st);
 }
 
 }  // namespace ggufb200

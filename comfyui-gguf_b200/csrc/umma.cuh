@@ -110,10 +110,10 @@ __device__ __forceinline__ uint64_t g2_desc_sw128(uint32_t smem_addr)
     return d;
 }
 // kind::f16 instruction descriptor, D = f32, A/B K-major, UMMA M = 256 (pair), N = 256
-template <int ACT> __device__ __forceinline__ constexpr uint32_t g2_idesc()
+template <int ACT, int UN = kG2BN> __device__ __forceinline__ constexpr uint32_t g2_idesc()
 {
     uint32_t fmt = ACT == kBF16 ? 1u : 0u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kG2BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 template <int ACT> __device__ __forceinline__ float g2_bias(const void *bias, int bias_dtype, long long n)
 {
@@ -152,13 +152,13 @@ static inline G2EncodeFn g2_encode_fn()
     return fn;
 }
 
-static inline bool g2_make_map(CUtensorMap *tm, const void *base, long long rows, long long K, long long ld, int act)
+static inline bool g2_make_map(CUtensorMap *tm, const void *base, long long rows, long long K, long long ld, int act, int box_rows = 128)
 {
     G2EncodeFn fn = g2_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kG2BK, 128u};
+    cuuint32_t box[2] = {(cuuint32_t)kG2BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapDataType dt = act == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     return fn(tm, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
