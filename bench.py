@@ -51,11 +51,47 @@ def measured_peak():
 
 
 def host_threads():
-    """Host cores this process may actually use (cgroup / affinity aware; os.cpu_count() over-reports in containers)."""
+    """Host threads this process can really run: affinity mask, capped by the cgroup CPU quota (containers routinely expose
+    more logical CPUs than they may use; oversubscribing the OpenMP team there is several times slower)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    n = min(n, max(1, q // int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+def pick_oracle_threads():
+    """OpenMP team size for the CPU legs: the candidate (all usable threads, or half of them when SMT siblings / quotas make
+    the full count slower) that dequantises a probe tensor fastest."""
+    import gguf
+    import oracle
+    full = host_threads()
+    probe = oracle.random_blocks(int(gguf.GGMLQuantizationType.Q8_0), 1 << 19, seed=1)
+    best_n, best_t = full, None
+    for n in sorted({full, max(1, full // 2)}, reverse=True):
+        oracle.set_num_threads(n)
+        oracle.dequant(probe, 8)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            oracle.dequant(probe, 8)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t * 0.9:
+            best_n, best_t = n, dt
+    oracle.set_num_threads(best_n)
+    return best_n
 
 
 def alg_bytes(qname, n_elems, out_bytes=2):
@@ -117,7 +153,7 @@ def cpu_baseline_run(budget_s=12.0, threads=None):
     import gguf
     import oracle
     # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every host core explicitly
-    oracle.set_num_threads(threads or host_threads())
+    oracle.set_num_threads(threads) if threads else pick_oracle_threads()
     cores = oracle.num_threads()
     N, K = 3072, 3072
     tensors = []
@@ -157,7 +193,7 @@ def run_reference(args):
         return
     import oracle
     import gguf
-    oracle.set_num_threads(host_threads())   # torchrun sets OMP_NUM_THREADS=1 for its workers
+    pick_oracle_threads()   # torchrun sets OMP_NUM_THREADS=1 for its workers: choose the team size explicitly
     N, K = 3072, 3072
     tensors = []
     for q in QTYPES:
