@@ -282,6 +282,82 @@ __device__ __forceinline__ void dequant_elems(const uint8_t *blk, int e0, const 
     }
 }
 
+// ---------------------------------------------------------------- specialised 16-element producers (fused GEMM hot formats)
+// Sixteen consecutive elements (e0 % 16 == 0) of one block as eight packed activation-dtype pairs, fp16 reference math.
+// Same operations and roundings as group_scale + dequant_elems, but with the whole header fetched by one 16-byte load, the
+// quants by one 16-byte load and (d,dmin) x (sc,mn) as a single half2 multiply.  `blk` must be 16-byte aligned.
+template <class Q, int ACT> struct Fast16 {
+    static constexpr bool available = false;
+};
+
+template <int ACT> __device__ __forceinline__ uint32_t pack_h2_to_act(__half2 v)
+{
+    if constexpr (ACT == kF16) {
+        return *reinterpret_cast<uint32_t *>(&v);
+    } else {
+        float2 f = __half22float2(v);
+        __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+        return *reinterpret_cast<uint32_t *>(&b);
+    }
+}
+
+template <int ACT> struct Fast16<Block<T_Q4_K>, ACT> {
+    static constexpr bool available = true;
+    static __device__ __forceinline__ void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
+    {
+        const uint4 h = *reinterpret_cast<const uint4 *>(blk);                 // d | dmin<<16, scales[0..11]
+        const int sb = e0 >> 5;                                               // sub-block 0..7
+        const uint4 qw = *reinterpret_cast<const uint4 *>(blk + 16 + 32 * (e0 >> 6) + (e0 & 16));
+        // 6-bit scale / min of the sub-block (dequant.py:129-139), branch-free on the three scale words
+        const int sh = 8 * (sb & 3);
+        const uint32_t a = (h.y >> sh) & 0xFFu, b = (h.z >> sh) & 0xFFu, c = (h.w >> sh) & 0xFFu;
+        const bool hi4 = sb >= 4;
+        const uint32_t sc = hi4 ? ((c & 0x0Fu) | ((a >> 6) << 4)) : (a & 63u);
+        const uint32_t mn = hi4 ? ((c >> 4) | ((b >> 6) << 4)) : (b & 63u);
+        // (sc, mn) -> exact fp16 pair through the 1024+u exponent pattern, then (d*sc, dmin*mn) in ONE rounded half2 multiply
+        uint32_t scm_bits = sc | (mn << 16) | 0x64006400u;
+        const __half2 k1024 = __half2half2(__ushort_as_half((unsigned short)0x6400u));
+        const __half2 scm = __hsub2_rn(*reinterpret_cast<__half2 *>(&scm_bits), k1024);
+        uint32_t dm_bits = h.x;
+        const __half2 DM = __hmul2_rn(*reinterpret_cast<__half2 *>(&dm_bits), scm);
+        const __half2 D2 = __low2half2(DM), M2 = __high2half2(DM);
+        const int nib = 4 * (sb & 1);                                         // odd sub-blocks live in the high nibbles
+        const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t v = (w[i] >> nib) & 0x0F0F0F0Fu;
+            uint32_t l = prmt(v, 0x64646464u, 0x4140u), u = prmt(v, 0x64646464u, 0x4342u);
+            __half2 lo = __hsub2_rn(*reinterpret_cast<__half2 *>(&l), k1024);
+            __half2 up = __hsub2_rn(*reinterpret_cast<__half2 *>(&u), k1024);
+            lo = __hsub2_rn(__hmul2_rn(D2, lo), M2);
+            up = __hsub2_rn(__hmul2_rn(D2, up), M2);
+            out[2 * i] = pack_h2_to_act<ACT>(lo);
+            out[2 * i + 1] = pack_h2_to_act<ACT>(up);
+        }
+    }
+};
+
+template <int ACT> struct Fast16<Block<T_Q8_0>, ACT> {
+    static constexpr bool available = true;
+    // a 34-byte block is only 2-byte aligned: assemble the sixteen int8 from 16-bit loads
+    static __device__ __forceinline__ void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
+    {
+        const uint16_t *p16 = reinterpret_cast<const uint16_t *>(blk);
+        const __half2 D2 = __half2half2(__ushort_as_half(p16[0]));
+        const __half2 k1152 = __half2half2(__ushort_as_half((unsigned short)(0x6400u + 128u)));
+        const uint16_t *q = p16 + 1 + (e0 >> 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t v = ((uint32_t)q[2 * i] | ((uint32_t)q[2 * i + 1] << 16)) ^ 0x80808080u;   // int8 + 128 as bytes
+            uint32_t l = prmt(v, 0x64646464u, 0x4140u), u = prmt(v, 0x64646464u, 0x4342u);
+            __half2 lo = __hmul2_rn(D2, __hsub2_rn(*reinterpret_cast<__half2 *>(&l), k1152));
+            __half2 up = __hmul2_rn(D2, __hsub2_rn(*reinterpret_cast<__half2 *>(&u), k1152));
+            out[2 * i] = pack_h2_to_act<ACT>(lo);
+            out[2 * i + 1] = pack_h2_to_act<ACT>(up);
+        }
+    }
+};
+
 template <class Q, int MATH, int N>
 __device__ __forceinline__ void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
 {

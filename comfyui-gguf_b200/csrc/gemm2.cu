@@ -206,16 +206,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint8_t *blk = STAGED ? packed + ((kb >> 2) & 1) * Cfg::PACKED_BYTES + row * SEG + (kin / Q::BS) * Q::TS
                                                 : wrow + (k / Q::BS) * Q::TS;
                     const int e0 = (int)(k % Q::BS);
-                    const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
-                    GroupScale<MATH> g1 = g0;
-                    if constexpr (GROUP == 16 && CPT == 4) g1 = group_scale<Q, MATH>(blk, e0 + 16);
+                    if constexpr (STAGED && CPT == 2 && MATH == kF16 && Fast16<Q, ACT>::available) {
+                        uint32_t o[8];
+                        Fast16<Q, ACT>::run(blk, e0, o);                  // hand-scheduled 16-element producer
+                        st_shared_v4(b_row + (((half * 2) ^ (row & 7)) << 4), o[0], o[1], o[2], o[3]);
+                        st_shared_v4(b_row + (((half * 2 + 1) ^ (row & 7)) << 4), o[4], o[5], o[6], o[7]);
+                    } else {
+                        const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
+                        GroupScale<MATH> g1 = g0;
+                        if constexpr (GROUP == 16 && CPT == 4) g1 = group_scale<Q, MATH>(blk, e0 + 16);
 #pragma unroll
-                    for (int c = 0; c < CPT; ++c) {
-                        typename Math<MATH>::T2 v[4];
-                        dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
-                        const int chunk = half * CPT + c;
-                        st_shared_v4(b_row + ((chunk ^ (row & 7)) << 4), pack16<ACT, MATH>(v[0]), pack16<ACT, MATH>(v[1]),
-                                     pack16<ACT, MATH>(v[2]), pack16<ACT, MATH>(v[3]));
+                        for (int c = 0; c < CPT; ++c) {
+                            typename Math<MATH>::T2 v[4];
+                            dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
+                            const int chunk = half * CPT + c;
+                            st_shared_v4(b_row + ((chunk ^ (row & 7)) << 4), pack16<ACT, MATH>(v[0]), pack16<ACT, MATH>(v[1]),
+                                         pack16<ACT, MATH>(v[2]), pack16<ACT, MATH>(v[3]));
+                        }
                     }
                 } else {
 #pragma unroll
