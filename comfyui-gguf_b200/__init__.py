@@ -1,14 +1,19 @@
 """ggufb200: B200-native (sm_100a) drop-in for the dequant + Linear hot path of city96/ComfyUI-GGUF.
 
-Loaded by ComfyUI as a custom node directory (node classes exported when `comfy` is importable), or by path
-through `__graft_entry__.load_package()` for tests and benchmarks.
+ComfyUI imports this directory as a custom node package and reads NODE_CLASS_MAPPINGS / NODE_DISPLAY_NAME_MAPPINGS from it.
+Outside ComfyUI (tests, benchmarks, the GPU box) the host packages are absent and only the kernel-facing modules
+(`dequant`, `ops`, `loader`, `replicas`) are used, through `__graft_entry__.load_package()`.
 """
-try:
-    import comfy.utils  # noqa: F401
-    import folder_paths  # noqa: F401
-except ImportError:
-    pass
-else:  # pragma: no cover - only inside ComfyUI
-    from .nodes import NODE_CLASS_MAPPINGS
-    NODE_DISPLAY_NAME_MAPPINGS = {k: v.TITLE for k, v in NODE_CLASS_MAPPINGS.items()}
+import importlib.util as _ilu
+
+
+def _inside_comfyui() -> bool:
+    return all(_ilu.find_spec(name) is not None for name in ("comfy", "folder_paths", "nodes"))
+
+
+if _inside_comfyui():  # pragma: no cover - needs a ComfyUI checkout
+    from . import nodes as _nodes
+
+    NODE_CLASS_MAPPINGS = dict(_nodes.NODE_CLASS_MAPPINGS)
+    NODE_DISPLAY_NAME_MAPPINGS = {key: cls.TITLE for key, cls in NODE_CLASS_MAPPINGS.items()}
     __all__ = ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS"]

@@ -157,102 +157,113 @@ def linear_dense(x, weight, bias=None):
     return y.reshape(*x.shape[:-1], N)
 
 
+_BIG_EMBEDDING_ROWS = 64 * 1024     # loader threshold above which Embedding always takes the GGML load path (ops.py:116-117)
+_META = torch.device("meta")
+
+
+def _collect_patches(tensor):
+    """Flatten `tensor.patches` ([(patch_list, key), ...]) onto the tensor's device; returns (patches, last key)."""
+    gathered, key = [], None
+    for entries, key in getattr(tensor, "patches", []):
+        gathered.extend(move_patch_to_device(entries, tensor.device))
+    return gathered, key
+
+
 class GGMLLayer(torch.nn.Module):
-    """On-the-fly dequantising layer base (ops.py:93-225)."""
+    """Base of every GGUF-aware op: state-dict plumbing for packed tensors and on-the-fly weight materialisation.
+
+    Mirrors the reference class of the same name (ops.py:93-225): same attributes (`comfy_cast_weights`, `dequant_dtype`,
+    `patch_dtype`, `largest_layer`) and the same method names, because ComfyUI and the loader nodes address them by name."""
     comfy_cast_weights = True
     dequant_dtype = None
     patch_dtype = None
     largest_layer = False
     torch_compatible_tensor_types = {None, _Q.F32, _Q.F16}
 
+    # ------------------------------------------------------------------ predicates
     def is_ggml_quantized(self, *, weight=None, bias=None):
-        weight = self.weight if weight is None else weight
-        bias = self.bias if bias is None else bias
-        return is_quantized(weight) or is_quantized(bias)
+        w = self.weight if weight is None else weight
+        b = self.bias if bias is None else bias
+        return is_quantized(w) or is_quantized(b)
 
-    # ---- state dict plumbing (ops.py:110-164)
+    def _takes_ggml_load_path(self, weight, bias):
+        if isinstance(self, torch.nn.Linear):            # Linear never allocates, so it always loads by assignment
+            return True
+        if self.is_ggml_quantized(weight=weight, bias=bias):
+            return True
+        return isinstance(self, torch.nn.Embedding) and self.weight.shape[0] >= _BIG_EMBEDDING_ROWS
+
+    # ------------------------------------------------------------------ load: adopt the tensors of the state dict as they are
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        weight, bias = state_dict.get(f"{prefix}weight"), state_dict.get(f"{prefix}bias")
-        if self.is_ggml_quantized(weight=weight, bias=bias) or isinstance(self, torch.nn.Linear):
-            return self.ggml_load_from_state_dict(state_dict, prefix, *args, **kwargs)
-        if isinstance(self, torch.nn.Embedding) and self.weight.shape[0] >= (64 * 1024):
+        if self._takes_ggml_load_path(state_dict.get(prefix + "weight"), state_dict.get(prefix + "bias")):
             return self.ggml_load_from_state_dict(state_dict, prefix, *args, **kwargs)
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def ggml_load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
-        plen = len(prefix)
-        for key, value in state_dict.items():
-            name = key[plen:]
-            if name == "weight":
-                self.weight = torch.nn.Parameter(value, requires_grad=False)
-            elif name == "bias" and value is not None:
-                self.bias = torch.nn.Parameter(value, requires_grad=False)
+        cut = len(prefix)
+        for full_key, tensor in state_dict.items():
+            leaf = full_key[cut:]
+            if leaf == "weight" or (leaf == "bias" and tensor is not None):
+                # nn.Parameter(GGMLTensor) is the very same object: detach()/clone() return self
+                setattr(self, leaf, torch.nn.Parameter(tensor, requires_grad=False))
             else:
-                unexpected_keys.append(key)
-        if self.weight is None and isinstance(self, torch.nn.Linear):  # ops.py:131-134
-            self.weight = torch.nn.Parameter(torch.zeros(self.in_features, self.out_features), requires_grad=False)
+                unexpected_keys.append(full_key)
+        if isinstance(self, torch.nn.Linear) and self.weight is None:
+            placeholder = torch.zeros(self.in_features, self.out_features)      # shape quirk kept from ops.py:131-134
+            self.weight = torch.nn.Parameter(placeholder, requires_grad=False)
             missing_keys.append(prefix + "weight")
-        if getattr(self.weight, "is_largest_weight", False):  # ops.py:136-138
-            self.largest_layer = True
+        self.largest_layer = self.largest_layer or bool(getattr(self.weight, "is_largest_weight", False))
 
+    # ------------------------------------------------------------------ save: meta stand-ins for the host's VRAM estimate
     def _save_to_state_dict(self, *args, **kwargs):
-        if self.is_ggml_quantized():
-            return self.ggml_save_to_state_dict(*args, **kwargs)
-        return super()._save_to_state_dict(*args, **kwargs)
+        if not self.is_ggml_quantized():
+            return super()._save_to_state_dict(*args, **kwargs)
+        return self.ggml_save_to_state_dict(*args, **kwargs)
 
     def ggml_save_to_state_dict(self, destination, prefix, keep_vars):
-        """Meta-device stand-ins used by the host for VRAM estimation (ops.py:140-160)."""
-        meta = torch.device("meta")
-        destination[prefix + "weight"] = torch.zeros_like(self.weight, device=meta)
-        if self.bias is not None:
-            destination[prefix + "bias"] = torch.zeros_like(self.bias, device=meta)
+        for leaf in ("weight", "bias"):
+            tensor = getattr(self, leaf)
+            if tensor is not None:
+                destination[prefix + leaf] = torch.zeros_like(tensor, device=_META)
         if self.largest_layer:
-            # scratch the two-step route needs for the largest dequantised weight
-            shape = getattr(self.weight, "tensor_shape", self.weight.shape)
-            dt = self.dequant_dtype if self.dequant_dtype and self.dequant_dtype != "target" else torch.float16
-            destination[prefix + "temp.weight"] = torch.empty(*shape, device=meta, dtype=dt)
+            # room for the largest dequantised weight (the two-step route's scratch), reported like the reference does
+            logical = getattr(self.weight, "tensor_shape", self.weight.shape)
+            explicit = self.dequant_dtype not in (None, "target")
+            destination[prefix + "temp.weight"] = torch.empty(*logical, device=_META,
+                                                              dtype=self.dequant_dtype if explicit else torch.float16)
 
-    # ---- weight materialisation (ops.py:166-211)
+    # ------------------------------------------------------------------ weight materialisation (two-step route)
     def get_weight(self, tensor, dtype):
+        """Dequantise `tensor` (ONE kernel launch) and apply attached LoRA patches; returns a plain torch.Tensor."""
         if tensor is None:
             return None
-        patch_list, key = [], None
-        for patches, key in getattr(tensor, "patches", []):
-            patch_list += move_patch_to_device(patches, tensor.device)
-        weight = dequantize_tensor(tensor, dtype, self.dequant_dtype)   # one kernel launch
-        weight = _plain(weight)
-        if patch_list:
-            if self.patch_dtype is None:
-                weight = comfy_lora.calculate_weight(patch_list, weight, key)
-            else:
-                pdt = dtype if self.patch_dtype == "target" else self.patch_dtype
-                weight = comfy_lora.calculate_weight(patch_list, weight, key, pdt)
-        return weight
+        patches, key = _collect_patches(tensor)          # patches start moving to the device before the dequant launch
+        dense = _plain(dequantize_tensor(tensor, dtype, self.dequant_dtype))
+        if not patches:
+            return dense
+        if self.patch_dtype is None:
+            return comfy_lora.calculate_weight(patches, dense, key)
+        return comfy_lora.calculate_weight(patches, dense, key, dtype if self.patch_dtype == "target" else self.patch_dtype)
 
     @torch_compiler_disable()
     def cast_bias_weight(s, input=None, dtype=None, device=None, bias_dtype=None):
-        if input is not None:
-            if dtype is None:
-                dtype = getattr(input, "dtype", torch.float32)
-            if bias_dtype is None:
-                bias_dtype = dtype
-            if device is None:
-                device = input.device
-        non_blocking = comfy_mm.device_supports_non_blocking(device)
-        bias = None
-        if s.bias is not None:
-            bias = s.get_weight(s.bias.to(device), dtype)
-            bias = comfy_ops.cast_to(bias, bias_dtype, device, non_blocking=non_blocking, copy=False)
-        weight = s.get_weight(s.weight.to(device), dtype)
-        weight = comfy_ops.cast_to(weight, dtype, device, non_blocking=non_blocking, copy=False)
-        return weight, bias
+        if input is not None:                            # unspecified targets follow the activation
+            dtype = getattr(input, "dtype", torch.float32) if dtype is None else dtype
+            bias_dtype = dtype if bias_dtype is None else bias_dtype
+            device = input.device if device is None else device
+        async_ok = comfy_mm.device_supports_non_blocking(device)
 
+        def materialise(param, want):
+            dense = s.get_weight(param.to(device), dtype)
+            return comfy_ops.cast_to(dense, want, device, non_blocking=async_ok, copy=False)
+
+        bias = materialise(s.bias, bias_dtype) if s.bias is not None else None      # bias first, as in ops.py:205-207
+        return materialise(s.weight, dtype), bias
+
+    # ------------------------------------------------------------------ forward dispatch
     def forward_comfy_cast_weights(self, input, *args, **kwargs):
-        if self.is_ggml_quantized():
-            out = self.forward_ggml_cast_weights(input, *args, **kwargs)
-        else:
-            out = super().forward_comfy_cast_weights(input, *args, **kwargs)
-        return _plain(out)
+        route = self.forward_ggml_cast_weights if self.is_ggml_quantized() else super().forward_comfy_cast_weights
+        return _plain(route(input, *args, **kwargs))      # never leak the tensor subclass to the host
 
     def forward_ggml_cast_weights(self, input):
         raise NotImplementedError
