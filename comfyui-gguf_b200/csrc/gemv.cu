@@ -144,6 +144,26 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_mma_kernel(const uint8_t *_
             const long long k = kin ? kreal : 0;
             const uint8_t *b0p = w0 + (k / Q::BS) * Q::TS, *b1p = w1 + (k / Q::BS) * Q::TS;
             const int e0 = (int)(k % Q::BS);
+            if constexpr (MATH == kF16 && Fast16<Q, ACT>::available) {
+                // hand-scheduled producers (one 16-byte header load + one 16-byte quant load per 16 elements)
+#pragma unroll
+                for (int hseg = 0; hseg < 2; ++hseg) {
+                    uint32_t a[8], b[8];
+                    Fast16<Q, ACT>::run(b0p, e0 + hseg * 16, a);
+                    Fast16<Q, ACT>::run(b1p, e0 + hseg * 16, b);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        uint4 xv = make_uint4(0, 0, 0, 0);
+                        if (xrow_ok && kin) xv = *reinterpret_cast<const uint4 *>(xrow + (k + hseg * 16 + t * 8) * 2);
+                        const uint32_t a0 = (ok0 && kin) ? a[4 * t] : 0u, a1 = (ok0 && kin) ? a[4 * t + 1] : 0u;
+                        const uint32_t a2 = (ok0 && kin) ? a[4 * t + 2] : 0u, a3 = (ok0 && kin) ? a[4 * t + 3] : 0u;
+                        const uint32_t c0 = (ok1 && kin) ? b[4 * t] : 0u, c1 = (ok1 && kin) ? b[4 * t + 1] : 0u;
+                        const uint32_t c2 = (ok1 && kin) ? b[4 * t + 2] : 0u, c3 = (ok1 && kin) ? b[4 * t + 3] : 0u;
+                        mma_16x8x16<ACT>(d, a0, c0, a1, c1, xv.x, xv.y);
+                        mma_16x8x16<ACT>(d, a2, c2, a3, c3, xv.z, xv.w);
+                    }
+                }
+            } else {
             const GroupScale<MATH> ga0 = group_scale<Q, MATH>(b0p, e0), gb0 = group_scale<Q, MATH>(b1p, e0);
             GroupScale<MATH> ga1 = ga0, gb1 = gb0;
             if constexpr (GROUP == 16) {
@@ -165,6 +185,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_mma_kernel(const uint8_t *_
                 if (xrow_ok && kin) xv = *reinterpret_cast<const uint4 *>(xrow + (k + t * 8) * 2);
                 mma_16x8x16<ACT>(d, a[0], b[0], a[1], b[1], xv.x, xv.y);
                 mma_16x8x16<ACT>(d, a[2], b[2], a[3], b[3], xv.z, xv.w);
+            }
             }
         }
         // d[0]: (feature g, row 2c)  d[1]: (g, 2c+1)  d[2]: (g+8, 2c)  d[3]: (g+8, 2c+1)
@@ -245,7 +266,7 @@ static int gemv_launch(const void *W, long long N, long long K, const void *X, l
     const uint8_t *w = reinterpret_cast<const uint8_t *>(W);
     const uint8_t *x = reinterpret_cast<const uint8_t *>(X);
     uint8_t *y = reinterpret_cast<uint8_t *>(Y);
-    if (g_gemv_mma) {
+    if (g_gemv_mma && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {   // the 16-byte header / quant loads need an aligned base
         long long tiles = (N + 15) / 16;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);

@@ -146,3 +146,22 @@ def test_error_paths_raise(pkg):
         pkg.ops.linear_packed(torch.randn(2, 256, device=DEV, dtype=torch.bfloat16), w, None)
     with pytest.raises(pkg.lib.GGUFB200Error):
         pkg.ops.linear_packed(torch.randn(64, 512, device=DEV, dtype=torch.bfloat16), w, None, None, pkg.lib.ALGO_GEMV)
+
+
+@pytest.mark.parametrize("M", [2, 300])
+def test_unaligned_packed_weight_view(pkg, M):
+    """A packed weight that does not start on a 16-byte boundary (a byte-offset view): every 16-byte fast path (TMA staging,
+    Fast16 producers, bulk loads) must step aside for the alignment-agnostic routes and still match."""
+    qt, N, K = Q.Q4_K, 136, 1024
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    raw = oracle.random_blocks(int(qt), N * K // bs, seed=11, scale=0.02).reshape(-1)
+    buf = torch.zeros(raw.size + 64, dtype=torch.uint8, device=DEV)
+    buf[6:6 + raw.size] = torch.from_numpy(raw).to(DEV)
+    view = buf[6:6 + raw.size].view(N, K // bs * ts)
+    assert view.data_ptr() % 16 != 0
+    w = pkg.ops.GGMLTensor(view, tensor_type=qt, tensor_shape=torch.Size((N, K)))
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    want = oracle.linear(raw, int(qt), N, K, torch_bits(x), oracle.DT_BF16, oracle.DT_F16, None)
+    for algo in ((pkg.lib.ALGO_GEMV,) if M <= 8 else (pkg.lib.ALGO_FUSED_MMA, pkg.lib.ALGO_DEQUANT_MMA)):
+        y = pkg.ops.linear_packed(x, w, None, None, algo)
+        assert rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), 1)) <= TOL
