@@ -198,6 +198,14 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     if (!aligned16(X) || !aligned16(Y) || (ldx % 8) != 0 || (ldy % 8) != 0) return GGUFB200_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
 
+    // The GEMV / fused producers read the packed rows with the per-format natural alignment (up to 16 bytes).  A packed
+    // tensor that does not start on a 16-byte boundary (never produced by torch allocations, only by byte-offset views)
+    // is therefore always routed through the standalone dequant kernel, which stages any alignment, plus the dense GEMM.
+    if (!aligned16(W_packed)) {
+        if (!workspace || workspace_bytes < (size_t)N * (size_t)K * 2) return GGUFB200_E_ALIGN;
+        algo = GGUFB200_ALGO_DEQUANT_MMA;
+    }
+
     if (algo == GGUFB200_ALGO_AUTO) {
         const bool ws_ok = workspace && workspace_bytes >= (size_t)N * (size_t)K * 2;
         const bool fused_ok = gemm_fused_supported(ggml_type) && math_dtype == kF16 && (K % 64) == 0;

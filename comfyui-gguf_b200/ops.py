@@ -122,6 +122,8 @@ def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
             bias = bias.contiguous()
         bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
     L = _lib.lib()
+    if wraw.data_ptr() % 16 != 0:
+        algo = _lib.ALGO_DEQUANT_MMA      # byte-offset view: only the standalone dequant stages arbitrary alignment
     ws, ws_ptr, ws_bytes = None, None, 0
     need = L.ggufb200_linear_workspace(int(qtype), M, N, K, act, algo)
     if need:

@@ -111,7 +111,8 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
  *               reference's rounding sequence and then cast to act_dtype, exactly the
  *               weight the reference hands to F.linear; accumulation is fp32
  *   bias        NULL or N values of bias_dtype (0/1/2)
- *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0)
+ *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0).  A W_packed that is
+ *               not 16-byte aligned is always served by GGUFB200_ALGO_DEQUANT_MMA and needs that algo's workspace
  *   algo        GGUFB200_ALGO_*
  */
 size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo);
