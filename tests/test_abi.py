@@ -70,3 +70,22 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
     monkeypatch.setattr(pkg.lib, "LIB_PATH", "/nonexistent/libggufb200.so")
     with pytest.raises(pkg.lib.GGUFB200Error):
         pkg.lib.lib()
+
+
+def test_tuning_keys_and_gemm_validation_without_gpu(pkg):
+    L = pkg.lib.lib()
+    for key, value in ((0, 4), (1, 1), (2, 2), (3, 0), (4, 1), (5, 1)):
+        assert L.ggufb200_set_tuning(key, value) == 0
+    assert L.ggufb200_set_tuning(99, 1) == -8                      # unknown knob
+    L.ggufb200_set_tuning(0, 0)
+    buf = (ctypes.c_uint8 * 4096)()
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    # ggufb200_gemm: dtype must be 16-bit, leading dimensions >= K and multiples of 8, pointers aligned
+    assert L.ggufb200_gemm(p16, 8, 64, 64, p16, 4, 64, 2, None, 0, p16, 8, None) == -2
+    assert L.ggufb200_gemm(p16, 8, 64, 32, p16, 4, 64, 1, None, 0, p16, 8, None) == -4
+    assert L.ggufb200_gemm(p16 + 2, 8, 64, 64, p16, 4, 64, 1, None, 0, p16, 8, None) == -3
+    assert L.ggufb200_gemm(p16, 8, 64, 64, p16, 0, 64, 1, None, 0, p16, 8, None) == 0   # M == 0 is a no-op
+    # ggufb200_linear: an unaligned packed weight needs the dequant+GEMM workspace
+    assert L.ggufb200_linear(int(Q.Q4_K), p16 + 2, 8, 256, p16, 4, 256, 1, 0, None, 0, p16, 8, None, 0, 0, None) == -3
+    # row gather: K must be a multiple of the block size
+    assert L.ggufb200_dequant_rows(int(Q.Q4_K), p16, 4, 100, p16, 1, p16, 0, 0, None) == -4

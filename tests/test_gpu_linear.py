@@ -165,3 +165,35 @@ def test_unaligned_packed_weight_view(pkg, M):
     for algo in ((pkg.lib.ALGO_GEMV,) if M <= 8 else (pkg.lib.ALGO_FUSED_MMA, pkg.lib.ALGO_DEQUANT_MMA)):
         y = pkg.ops.linear_packed(x, w, None, None, algo)
         assert rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), 1)) <= TOL
+
+
+def test_conv2d_and_norms_with_quantised_parameters(pkg):
+    """Non-Linear consumers of the standalone dequant (ops.py:246-271): Conv2d with a Q8_0 kernel, LayerNorm / GroupNorm with
+    BF16-typed affine parameters.  Reference semantics = the stock functional op on the dequantised parameters."""
+    ops = pkg.ops.GGMLOps
+    g = torch.Generator(device=DEV).manual_seed(0)
+    # Conv2d: logical weight [8, 32, 3, 3] = 2304 elements = 72 Q8_0 blocks
+    raw = oracle.random_blocks(int(Q.Q8_0), 72, seed=21, scale=0.02)
+    w = pkg.ops.GGMLTensor(torch.from_numpy(raw).to(DEV), tensor_type=Q.Q8_0, tensor_shape=torch.Size((8, 32, 3, 3)))
+    b = pkg.ops.GGMLTensor(torch.randn(8, device=DEV, generator=g), tensor_type=Q.F32, tensor_shape=torch.Size((8,)))
+    conv = ops.Conv2d(32, 8, 3, padding=1, device="meta")
+    conv.load_state_dict({"weight": w, "bias": b}, assign=True)
+    x = torch.randn(2, 32, 16, 16, device=DEV, generator=g).to(torch.bfloat16)
+    y = conv(x)
+    W = torch.from_numpy(oracle.dequant(raw, int(Q.Q8_0), oracle.DT_BF16, oracle.DT_F16).view(np.int16)).to(DEV).view(torch.bfloat16).reshape(8, 32, 3, 3)
+    ref = torch.nn.functional.conv2d(x, W, b.as_subclass(torch.Tensor).to(torch.bfloat16), padding=1)
+    assert type(y) is torch.Tensor and torch.equal(y, ref)
+
+    def bf16_param(n, seed):
+        v = (torch.randn(n, generator=torch.Generator().manual_seed(seed)) * 0.5 + 1).to(torch.bfloat16)
+        return v, pkg.ops.GGMLTensor(v.view(torch.uint8).to(DEV), tensor_type=Q.BF16, tensor_shape=torch.Size((n,)))
+    wv, wq = bf16_param(64, 1)
+    bv, bq = bf16_param(64, 2)
+    ln = ops.LayerNorm(64, device="meta")
+    ln.load_state_dict({"weight": wq, "bias": bq}, assign=True)
+    xs = torch.randn(5, 64, device=DEV, generator=g).to(torch.float16)
+    torch.testing.assert_close(ln(xs), torch.nn.functional.layer_norm(xs, (64,), wv.to(DEV).half(), bv.to(DEV).half(), ln.eps))
+    gn = ops.GroupNorm(8, 64, device="meta")
+    gn.load_state_dict({"weight": wq, "bias": bq}, assign=True)
+    xg = torch.randn(2, 64, 4, 4, device=DEV, generator=g).to(torch.float16)
+    torch.testing.assert_close(gn(xg), torch.nn.functional.group_norm(xg, 8, wv.to(DEV).half(), bv.to(DEV).half(), gn.eps))
