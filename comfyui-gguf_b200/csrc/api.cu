@@ -7,6 +7,7 @@ extern int g_dequant_ctas_per_sm;
 extern int g_dequant_pdl;
 extern int g_fused_staged;
 extern int g_gemv_mma;
+extern int g_fused_splitk;
 int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st);
 int unpack_dispatch(int type, const void *packed, long long n_blocks, int16_t *q, int16_t *sc, int16_t *mn, cudaStream_t st);
 int rows_dispatch(int type, const void *packed, long long n_table_rows, long long K, const long long *rows, long long n_rows,
@@ -18,7 +19,8 @@ int gemm_fused_dispatch(int type, const void *W, long long N, long long K, const
 int gemm_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                         int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
-                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st);
+int gemm2_fused_splits(long long M, long long N, long long K);
 int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                          int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
@@ -34,11 +36,27 @@ static int g_auto_fused = 0;     // large-M route picked by GGUFB200_ALGO_AUTO: 
 static int g_gemm_variant = 2;   // ggufb200_set_tuning(2, v)
 
 static int fused_mma(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, int math,
-                     const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+                     const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    return g_gemm_variant >= 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st)
+    return g_gemm_variant >= 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, ws, ws_bytes, st)
                                : gemm_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st);
 }
+// GGUFB200_ALGO_AUTO for M > 8, measured on B200 (profiles/): with M >= ~1k the dequant-once + dense GEMM route wins
+// (1.27-1.44 vs 0.87-1.21 PFLOP/s); for short activations the fused kernel wins because the standalone dequant is no longer
+// amortised over many M tiles (and split-K keeps all SM pairs busy while every packed byte is still read once).
+static bool auto_prefers_fused(int type, long long M, long long N, long long K)
+{
+    if (!gemm_fused_supported(type) || (K % 64) != 0) return false;
+    if (g_auto_fused) return true;
+    if (M > 1024) return false;
+    if (g_gemm_variant >= 1) {   // split-K: all SM pairs dequantise in parallel (measured: profiles/r01_bench_linear_smallm.log)
+        const int splits = gemm2_fused_splits(M, N, K);
+        if (splits >= 4 || (splits >= 2 && K >= 2 * N)) return true;
+        if (splits >= 2) return false;
+    }
+    return M > 256 && N >= 12288;
+}
+
 static int dense_mma(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act,
                      const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
@@ -138,6 +156,10 @@ int ggufb200_set_tuning(int key, int value)
         g_gemv_mma = value ? 1 : 0;
         return GGUFB200_OK;
     }
+    if (key == 6) {
+        g_fused_splitk = value ? 1 : 0;
+        return GGUFB200_OK;
+    }
     return GGUFB200_E_UNSUPPORTED;
 }
 
@@ -179,8 +201,10 @@ size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K,
 {
     if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0) return 0;
     const size_t dense = (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
+    const size_t splitk = (g_gemm_variant >= 1 && gemm_fused_supported(ggml_type) && gemm2_fused_splits(M, N, K) > 1) ? (size_t)M * (size_t)N * 4 : 0;
     if (algo == GGUFB200_ALGO_DEQUANT_MMA) return dense;
-    if (algo == GGUFB200_ALGO_AUTO && M > gemv_max_m() && !(g_auto_fused && gemm_fused_supported(ggml_type))) return dense;
+    if (algo == GGUFB200_ALGO_FUSED_MMA) return splitk;          // fp32 accumulation buffer of the split-K fused kernel
+    if (algo == GGUFB200_ALGO_AUTO && M > gemv_max_m()) return auto_prefers_fused(ggml_type, M, N, K) ? splitk : dense;
     return 0;
 }
 
@@ -210,10 +234,7 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
         const bool ws_ok = workspace && workspace_bytes >= (size_t)N * (size_t)K * 2;
         const bool fused_ok = gemm_fused_supported(ggml_type) && math_dtype == kF16 && (K % 64) == 0;
         if (M <= gemv_max_m()) algo = GGUFB200_ALGO_GEMV;
-        // measured on B200 (profiles/): with M >= ~1k the dequant-once + dense GEMM route wins (1.27-1.41 vs 0.86-1.15
-        // PFLOP/s); for short activations against a wide weight the fused kernel wins because the standalone dequant is
-        // no longer amortised over many M tiles
-        else if (fused_ok && (g_auto_fused || !ws_ok || (M <= 1024 && N >= 8192))) algo = GGUFB200_ALGO_FUSED_MMA;
+        else if (fused_ok && (auto_prefers_fused(ggml_type, M, N, K) || !ws_ok)) algo = GGUFB200_ALGO_FUSED_MMA;
         else algo = GGUFB200_ALGO_DEQUANT_MMA;
     }
     switch (algo) {
@@ -221,7 +242,7 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
         return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
     case GGUFB200_ALGO_FUSED_MMA:
         if (!gemm_fused_supported(ggml_type)) return GGUFB200_E_UNSUPPORTED;
-        return fused_mma(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+        return fused_mma(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace, workspace_bytes, st);
     case GGUFB200_ALGO_DEQUANT_MMA: {
         size_t need = (size_t)N * (size_t)K * 2;
         if (!workspace || workspace_bytes < need) return GGUFB200_E_WORKSPACE;

@@ -56,6 +56,10 @@ struct Gemm2Params {
     uint8_t *Y;
     long long ldy;
     int tiles_m;
+    int n_tiles;       // tiles_m * tiles_n
+    int kb_per_split;  // k-blocks per split (a multiple of 4); == K/64 when the K loop is not split
+    float *partial;    // split-K: fp32 [M, N] accumulation buffer (zeroed by the host), else nullptr
+    int splits;        // host side only
 };
 
 // STAGED (FUSED only): the packed rows of the CTA's B half are staged through shared memory by a 2-D TMA over the raw
@@ -91,11 +95,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
-    const int tile_m = pair % p.tiles_m;
-    const int tile_n = pair / p.tiles_m;
+    const int tile = pair % p.n_tiles;
+    const int split = pair / p.n_tiles;             // split-K: this pair owns k-blocks [kb0, kb0 + num_kb)
+    const int tile_m = tile % p.tiles_m;
+    const int tile_n = tile / p.tiles_m;
     const long long m0 = (long long)tile_m * (256 * ACCS);
     const long long n0 = (long long)tile_n * kG2BN;
-    const int num_kb = (int)(p.K / kG2BK);
+    const int kb0 = split * p.kb_per_split;
+    const int num_kb = min(p.kb_per_split, (int)(p.K / kG2BK) - kb0);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -121,11 +128,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) {
         // ===================== TMA producer (each CTA loads its own rows; bytes are credited to the leader's barrier)
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int kb = kb0 + i;    // ring slots / parities follow the local index i, K coordinates the global kb
                 if constexpr (STAGED) {
-                    if ((kb & 3) == 0) {   // next 256-wide K-span of this CTA's 128 packed rows
-                        const int span = kb >> 2, pb = span & 1;
-                        mbar_wait(&empty_p[pb], (uint32_t)(((span >> 1) & 1) ^ 1));
+                    if ((i & 3) == 0) {   // next 256-wide K-span of this CTA's 128 packed rows
+                        const int lspan = i >> 2, pb = lspan & 1, span = kb >> 2;
+                        mbar_wait(&empty_p[pb], (uint32_t)(((lspan >> 1) & 1) ^ 1));
                         mbar_arrive_expect_tx(&full_p[pb], 128 * SEG);
                         asm volatile(
                             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -135,8 +143,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             : "memory");
                     }
                 }
-                const int s = kb % STAGES;
-                mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
+                const int s = i % STAGES;
+                mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
                 uint8_t *a_dst = tiles + s * Cfg::STAGE_BYTES;
                 const uint32_t bar = mapa_u32(smem_u32(&full_a[s]), 0);
                 if (leader) mbar_arrive_expect_tx(&full_a[s], 2 * (FUSED ? Cfg::A_BYTES : Cfg::STAGE_BYTES));
@@ -150,7 +158,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ===================== MMA issuer: leader CTA, one thread, drives the tensor cores of both SMs
         if (leader && lane == 0) {
             constexpr uint32_t idesc = g2_idesc<ACT>();
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; ++kb) {   // local index: only ring slot / parity / first-MMA flag depend on it
                 const int s = kb % STAGES;
                 const uint32_t par = (uint32_t)((kb / STAGES) & 1);
                 mbar_wait_cluster(&full_a[s], par);
@@ -193,17 +201,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const bool valid = n < p.N;
             const uint8_t *wrow = p.W + (valid ? n : 0) * p.row_bytes;
             constexpr int GROUP = GroupOf<Q>::value;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
+            for (int i = 0; i < num_kb; ++i) {
+                const int kb = kb0 + i;
+                const int s = i % STAGES;
                 if constexpr (STAGED) {
-                    if ((kb & 3) == 0) mbar_wait(&full_p[(kb >> 2) & 1], (uint32_t)((kb >> 3) & 1));
+                    if ((i & 3) == 0) mbar_wait(&full_p[(i >> 2) & 1], (uint32_t)((i >> 3) & 1));
                 }
-                mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) & 1) ^ 1));
+                mbar_wait(&empty[s], (uint32_t)(((i / STAGES) & 1) ^ 1));
                 const uint32_t b_row = smem_u32(tiles + s * Cfg::STAGE_BYTES + Cfg::A_BYTES) + row * 128;
                 if (valid || STAGED) {   // STAGED: rows past N were zero-filled by the TMA and dequantise to 0
                     const long long k = (long long)kb * kG2BK + half * (CPT * 8);
                     const int kin = STAGED ? (int)(k & (kG2Span - 1)) : 0;   // position inside the staged span
-                    const uint8_t *blk = STAGED ? packed + ((kb >> 2) & 1) * Cfg::PACKED_BYTES + row * SEG + (kin / Q::BS) * Q::TS
+                    const uint8_t *blk = STAGED ? packed + ((i >> 2) & 1) * Cfg::PACKED_BYTES + row * SEG + (kin / Q::BS) * Q::TS
                                                 : wrow + (k / Q::BS) * Q::TS;
                     const int e0 = (int)(k % Q::BS);
                     if constexpr (STAGED && CPT == 2 && MATH == kF16 && Fast16<Q, ACT>::available) {
@@ -236,7 +245,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (lane == 0) {
                     mbar_arrive(&full_b[s]);
                     if constexpr (STAGED) {
-                        if ((kb & 3) == 3) mbar_arrive(&empty_p[(kb >> 2) & 1]);   // done with this packed buffer
+                        if ((i & 3) == 3) mbar_arrive(&empty_p[(i >> 2) & 1]);   // done with this packed buffer
                     }
                 }
             }
@@ -278,6 +287,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t r[32];
             g2_tmem_ld32(taddr0 + c0, r);
             g2_tmem_ld_wait();
+            if (p.partial) {
+                // split-K: add this pair's fp32 partial tile into the shared accumulation buffer (bias / cast happen in the
+                // finalize kernel).  Same transpose trick, 128-byte rows: eight lanes cover one row with red.global.add.v4.f32.
+                constexpr int PITCH32 = 144;
+                const uint32_t stage32 = smem_u32(tiles) + (uint32_t)warp * (32 * PITCH32);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) st_shared_v4(stage32 + lane * PITCH32 + g * 16, r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int chunk = lane + 32 * q;          // 256 chunks of 16 B = 32 rows x 8
+                    const int row = chunk >> 3, part = chunk & 7;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stage32 + row * PITCH32 + part * 16));
+                    const long long m = m_base + row;
+                    const long long n = n0 + c0 + part * 4;
+                    if (m < p.M && n < p.N)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.partial + m * p.N + n), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                __syncwarp();
+                continue;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint32_t o[4];
@@ -342,6 +373,64 @@ static int g2_pick_accs(long long M, long long N, bool fused = false)
     return eff(2) + 0.10 >= eff(1) ? 2 : 1;
 }
 
+// split-K finalize: Y = act(P + bias)
+template <int ACT>
+__global__ void __launch_bounds__(256) g2_finalize_kernel(const float *__restrict__ P, const void *__restrict__ bias, int bias_dtype,
+                                                          uint8_t *__restrict__ Y, long long M, long long N, long long ldy)
+{
+    const long long n8 = N / 8;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < M * n8; i += (long long)gridDim.x * 256) {
+        const long long m = i / n8, n = (i % n8) * 8;
+        const float4 a = *reinterpret_cast<const float4 *>(P + m * N + n), b = *reinterpret_cast<const float4 *>(P + m * N + n + 4);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += g2_bias<ACT>(bias, bias_dtype, n + j);
+        }
+        st_global_v4(Y + (m * ldy + n) * 2, g2_pack<ACT>(v[0], v[1]), g2_pack<ACT>(v[2], v[3]), g2_pack<ACT>(v[4], v[5]), g2_pack<ACT>(v[6], v[7]));
+    }
+}
+
+// Split-K factor of the fused kernel: short activations give too few (256*ACCS x 256) tiles for the 74 SM pairs, so the K
+// loop is cut into S ranges of whole 256-wide spans, each handled by its own pair (every packed byte is still read and
+// dequantised exactly once).  Returns 1 when splitting does not apply.
+int g_fused_splitk = 1;   // ggufb200_set_tuning(6, v)
+
+// Tiling of the fused kernel: ACCS (256 or 512 activation rows per pair) and the split-K factor.
+// Short activations give too few (256*ACCS x 256) tiles for the 74 SM pairs, so the K loop is cut into S ranges of whole
+// 256-wide spans, each handled by its own pair, and the fp32 partial tiles are summed in the caller's workspace.  The fused
+// kernel is bound by its dequant producers, and every M tile dequantises its W tile again, so when splitting is possible
+// the tallest tile (ACCS = 2) wins: each packed byte is then read and dequantised once per 512 activation rows.
+struct G2Plan {
+    int accs, splits;
+};
+
+static G2Plan g2_fused_plan(long long M, long long N, long long K, bool can_split)
+{
+    G2Plan plan{g2_pick_accs(M, N, true), 1};
+    if (!can_split || !g_fused_splitk || K % kG2Span != 0) return plan;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long pairs = sms / 2;
+    const long long tiles_n = (N + kG2BN - 1) / kG2BN;
+    auto tiles = [&](int accs) { return ((M + 256 * accs - 1) / (256 * accs)) * tiles_n; };
+    if (M > 256 && tiles(2) * 2 <= pairs) plan.accs = 2;
+    const long long t = tiles(plan.accs);
+    if (t * 2 > pairs) return plan;
+    const long long spans = K / kG2Span;
+    long long s = pairs / t;
+    if (s > spans) s = spans;
+    if (s > 16) s = 16;
+    if (s < 2) return plan;
+    const long long per = (spans + s - 1) / s;
+    plan.splits = (int)((spans + per - 1) / per);
+    return plan;
+}
+
+// split-K factor the fused route would use given a workspace (ggufb200_linear_workspace / AUTO routing)
+int gemm2_fused_splits(long long M, long long N, long long K) { return g2_fused_plan(M, N, K, true).splits; }
+
 template <class Q, int MATH, int ACT, int ACCS, bool STAGED = false>
 static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2Params &p, cudaStream_t st)
 {
@@ -355,8 +444,17 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
     Gemm2Params q = p;
     q.tiles_m = (int)((p.M + 256 * ACCS - 1) / (256 * ACCS));
     const long long tiles_n = (p.N + kG2BN - 1) / kG2BN;
+    q.n_tiles = (int)(q.tiles_m * tiles_n);
+    const int splits = p.partial ? p.splits : 1;
+    const int total_kb = (int)(p.K / kG2BK);
+    if (splits > 1) {
+        const int spans = (int)(p.K / kG2Span);
+        q.kb_per_split = ((spans + splits - 1) / splits) * 4;
+    } else {
+        q.kb_per_split = total_kb;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(2 * q.tiles_m * tiles_n));
+    cfg.gridDim = dim3((unsigned)(2 * q.n_tiles * splits));
     cfg.blockDim = dim3(STAGED ? 768 : kG2Threads);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
@@ -371,18 +469,42 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
 }
 
 template <class Q, int ACT>
+static int g2_fused_once(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
+                         void *Y, long long ldy, float *partial, G2Plan plan, cudaStream_t st);
+
+template <class Q, int ACT>
 static int g2_fused_act(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
-                        void *Y, long long ldy, cudaStream_t st)
+                        void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    // split-K needs the fp32 [M, N] accumulation buffer from the caller's workspace
+    const bool ws_ok = ws && ws_bytes >= (size_t)M * (size_t)N * 4 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
+    const G2Plan plan = g2_fused_plan(M, N, K, ws_ok);
+    if (plan.splits <= 1) return g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, nullptr, plan, st);
+    float *P = reinterpret_cast<float *>(ws);
+    if (cudaMemsetAsync(P, 0, (size_t)M * (size_t)N * 4, st) != cudaSuccess) return GGUFB200_E_CUDA;
+    int rc = g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, nullptr, 0, Y, ldy, P, plan, st);
+    if (rc != GGUFB200_OK) return rc;
+    long long work = M * (N / 8);
+    unsigned grid = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
+    g2_finalize_kernel<ACT><<<grid, 256, 0, st>>>(P, bias, bias_dtype, reinterpret_cast<uint8_t *>(Y), M, N, ldy);
+    return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <class Q, int ACT>
+static int g2_fused_once(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
+                         void *Y, long long ldy, float *partial, G2Plan plan, cudaStream_t st)
 {
     CUtensorMap tmA;
     if (!g2_make_map(&tmA, X, M, K, ldx, ACT)) return GGUFB200_E_CUDA;
     Gemm2Params p{};
+    p.partial = partial;
+    p.splits = plan.splits;
     p.W = reinterpret_cast<const uint8_t *>(W);
     p.row_bytes = K / Q::BS * Q::TS;
     p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.bias_dtype = bias_dtype;
     p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
-    const int accs = g2_pick_accs(M, N, true);
+    const int accs = plan.accs;
     constexpr int SEG = PackedSeg<Q>::value;
     if constexpr (SEG > 0) {
         // stage the packed rows through shared memory when a 2-D tensor map over the raw bytes is legal
@@ -408,13 +530,13 @@ static int g2_fused_act(const void *W, long long N, long long K, const void *X, 
 }
 
 int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
-                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
 {
     if (math_dtype != kF16 || K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
 #define GGUFB200_G2_CASE(T)                                                                                               \
     case T:                                                                                                               \
-        return act_dtype == kBF16 ? g2_fused_act<Block<T>, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st)        \
-                                  : g2_fused_act<Block<T>, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
+        return act_dtype == kBF16 ? g2_fused_act<Block<T>, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, st)  \
+                                  : g2_fused_act<Block<T>, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, st);
     switch (type) {
         GGUFB200_G2_CASE(T_Q4_0)
         GGUFB200_G2_CASE(T_Q4_1)

@@ -122,18 +122,26 @@ def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
             bias = bias.contiguous()
         bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
     L = _lib.lib()
+    math = math_code(dequant_dtype, x.dtype)
     if wraw.data_ptr() % 16 != 0:
         algo = _lib.ALGO_DEQUANT_MMA      # byte-offset view: only the standalone dequant stages arbitrary alignment
+    elif algo == _lib.ALGO_AUTO and M > GEMV_MAX_M and math != dtype_code(torch.float16):
+        algo = _lib.ALGO_DEQUANT_MMA      # the fused tensor-core producer is fp16-math only; size the workspace accordingly
     ws, ws_ptr, ws_bytes = None, None, 0
-    need = L.ggufb200_linear_workspace(int(qtype), M, N, K, act, algo)
+    qcode = int(qtype)
+    need = L.ggufb200_linear_workspace(qcode, M, N, K, act, algo)
     if need:
         ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         ws_ptr, ws_bytes = ws.data_ptr(), need
-    with torch.cuda.device(x.device):
-        rc = L.ggufb200_linear(int(qtype), wraw.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act,
-                               math_code(dequant_dtype, x.dtype), bias_ptr, bias_code, y.data_ptr(), N, ws_ptr, ws_bytes, algo,
-                               torch.cuda.current_stream(x.device).cuda_stream)
-    _lib.check(rc, f"ggufb200_linear({getattr(qtype, 'name', qtype)}, M={M}, N={N}, K={K})")
+    call = (qcode, wraw.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
+            ws_ptr, ws_bytes, algo)
+    if x.device.index == torch.cuda.current_device():     # the common case: skip the device-guard round trip
+        rc = L.ggufb200_linear(*call, torch.cuda.current_stream().cuda_stream)
+    else:
+        with torch.cuda.device(x.device):
+            rc = L.ggufb200_linear(*call, torch.cuda.current_stream(x.device).cuda_stream)
+    if rc:
+        _lib.check(rc, f"ggufb200_linear({getattr(qtype, 'name', qtype)}, M={M}, N={N}, K={K})")
     return y.reshape(*x.shape[:-1], N)
 
 
@@ -169,6 +177,36 @@ def _collect_patches(tensor):
     for entries, key in getattr(tensor, "patches", []):
         gathered.extend(move_patch_to_device(entries, tensor.device))
     return gathered, key
+
+
+def lora_side_terms(patches):
+    """Recognise a patch list that consists of plain LoRA deltas only.
+
+    `patches` is the flat list `_collect_patches` returns; entries follow comfy.lora's layout
+    `(strength_patch, value, strength_model[, offset, function])` with value `("lora", (up, down, alpha, mid, dora_scale,
+    reshape))` or a LoRAAdapter object carrying the same tuple in `.weights`.  Returns [(scale, up[N, r], down[r, K]), ...]
+    with scale = strength_patch * alpha / r, or None when any entry needs the general `calculate_weight` machinery
+    (strength_model != 1, offset / function hooks, LoCon mid weights, DoRA, reshape, diff / loha / lokr ... patches)."""
+    terms = []
+    for entry in patches:
+        if len(entry) < 3 or entry[2] != 1.0 or any(extra is not None for extra in entry[3:5]):
+            return None
+        value = entry[1]
+        if type(value).__name__ == "LoRAAdapter" and hasattr(value, "weights"):
+            payload = value.weights
+        elif isinstance(value, (tuple, list)) and len(value) == 2 and value[0] == "lora":
+            payload = value[1]
+        else:
+            return None
+        up, down = payload[0], payload[1]
+        alpha = payload[2] if len(payload) > 2 else None
+        if any(extra is not None for extra in payload[3:6]):
+            return None
+        if not (torch.is_tensor(up) and torch.is_tensor(down)) or up.dim() != 2 or down.dim() != 2 or up.shape[1] != down.shape[0]:
+            return None
+        scale = float(entry[0]) * (1.0 if alpha is None else float(alpha) / down.shape[0])
+        terms.append((scale, up, down))
+    return terms
 
 
 class GGMLLayer(torch.nn.Module):
@@ -282,14 +320,54 @@ class GGMLOps(comfy_ops.manual_cast):
             self.weight = None
             self.bias = None
 
+        # LoRA on a packed weight as rank-r side GEMMs on top of the packed-weight Linear (SURVEY 8f rank 1):
+        #   y = x W^T + b + sum_i scale_i (x down_i^T) up_i^T
+        # instead of dequantise + calculate_weight + F.linear on every forward (ops.py:171-190).  W + delta is then never
+        # rounded to the activation dtype, so the result differs from the reference by that one rounding (parity budget in
+        # tests/test_gpu_linear.py); set to False to get the reference's two-step arithmetic back.
+        lora_side_gemm = True
+
         def _fused_ok(self, input):
             w = self.weight
-            return (input.is_cuda and input.dtype in _FUSED_ACT and is_quantized(w) and not getattr(w, "patches", None)
+            return (input.is_cuda and input.dtype in _FUSED_ACT and is_quantized(w)
                     and not is_quantized(self.bias) and len(getattr(w, "tensor_shape", ())) == 2
                     and not getattr(self.bias, "patches", None))
 
+        def _lora_terms(self, dev):
+            """[] for an unpatched weight, the side-GEMM terms for a LoRA-only patch list, None -> two-step route."""
+            w = self.weight
+            if not getattr(w, "patches", None):
+                return []
+            if not self.lora_side_gemm or self.patch_dtype not in (None, "target"):
+                return None
+            entries = []
+            for patch_list, _key in w.patches:
+                entries.extend(patch_list)
+            terms = lora_side_terms(entries)
+            if terms is None:
+                return None
+            N, K = tuple(w.tensor_shape)
+            if any(tuple(up.shape) != (N, down.shape[0]) or down.shape[1] != K for _s, up, down in terms):
+                return None
+            return terms
+
+        def _add_lora(self, y, input, terms):
+            x2 = input.reshape(-1, input.shape[-1])
+            y2 = y.view(-1, y.shape[-1])
+            if len(terms) == 1:
+                scale, up, down = terms[0]
+                down_all = down.to(device=x2.device, dtype=x2.dtype, non_blocking=True)
+                up_all = up.to(device=x2.device, dtype=torch.float32, non_blocking=True) * scale
+            else:                                                   # one pair of GEMMs for any number of LoRAs
+                down_all = torch.cat([d.to(device=x2.device, dtype=x2.dtype, non_blocking=True) for _s, _u, d in terms], 0)
+                up_all = torch.cat([u.to(device=x2.device, dtype=torch.float32, non_blocking=True) * s for s, u, _d in terms], 1)
+            t = x2 @ down_all.t()                                   # [M, R]   library GEMMs: R is tens, not thousands
+            y2.addmm_(t, up_all.to(x2.dtype).t())
+            return y
+
         def forward_ggml_cast_weights(self, input):
-            if self._fused_ok(input):
+            terms = self._lora_terms(input.device) if self._fused_ok(input) else None
+            if terms is not None:
                 dev = input.device
                 w = self.weight if self.weight.device == dev else self.weight.to(dev)   # offloaded module: packed bytes H2D
                 b = self.bias
@@ -300,9 +378,11 @@ class GGMLOps(comfy_ops.manual_cast):
                 if w.tensor_type == _Q.BF16 and M > GEMV_MAX_M:
                     if input.dtype == torch.bfloat16 and K % 64 == 0:      # already dense: straight to the tensor-core GEMM
                         dense = _plain(w).view(torch.bfloat16).view(w.tensor_shape[0], K)
-                        return linear_dense(input, dense, b)
+                        y = linear_dense(input, dense, b)
+                        return self._add_lora(y, input, terms) if terms else y
                 elif M <= GEMV_MAX_M or (K % 64 == 0 and w.tensor_shape[0] % 8 == 0):
-                    return linear_packed(input, w, b, self.dequant_dtype)
+                    y = linear_packed(input, w, b, self.dequant_dtype)
+                    return self._add_lora(y, input, terms) if terms else y
             weight, bias = self.cast_bias_weight(input)
             return torch.nn.functional.linear(input, weight, bias)
 

@@ -112,7 +112,11 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
  *               weight the reference hands to F.linear; accumulation is fp32
  *   bias        NULL or N values of bias_dtype (0/1/2)
  *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0).  A W_packed that is
- *               not 16-byte aligned is always served by GGUFB200_ALGO_DEQUANT_MMA and needs that algo's workspace
+ *               not 16-byte aligned is always served by GGUFB200_ALGO_DEQUANT_MMA and needs that algo's workspace.
+ *               GGUFB200_ALGO_FUSED_MMA with few output tiles (short M) cuts K across SM pairs and accumulates fp32
+ *               partial tiles in the workspace (M*N*4 bytes); without it the kernel runs unsplit.  The size reported
+ *               for GGUFB200_ALGO_AUTO assumes math_dtype == fp16 (the reference default); with another math dtype
+ *               query and pass GGUFB200_ALGO_DEQUANT_MMA.
  *   algo        GGUFB200_ALGO_*
  */
 size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo);
@@ -135,7 +139,8 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
  *         1 = CTA-pair UMMA (cta_group::2), 0 = single-CTA UMMA,
  * key 3 = large-M route chosen by GGUFB200_ALGO_AUTO: 0 = dequant + GEMM (default, needs the workspace), 1 = fused,
  * key 4 = fused kernel stages the packed rows through shared memory with TMA when legal (default 1),
- * key 5 = small-M kernel: 1 = mma.sync tile kernel (default), 0 = warp-per-row FMA kernel. */
+ * key 5 = small-M kernel: 1 = mma.sync tile kernel (default), 0 = warp-per-row FMA kernel,
+ * key 6 = split-K of the fused kernel when the output has fewer tiles than SM pairs (default 1). */
 int ggufb200_set_tuning(int key, int value);
 
 #ifdef __cplusplus

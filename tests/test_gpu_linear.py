@@ -110,21 +110,73 @@ def test_offloaded_weight_is_moved_packed(pkg):
     assert y.is_cuda and rel_fro(y.float().cpu().numpy(), bits_to_f32(want.reshape(-1), 0)) <= TOL
 
 
-def test_lora_patched_weight_takes_two_step_route(pkg):
-    """tensor.patches present -> dequant + comfy.lora.calculate_weight + F.linear, as the reference does (ops.py:171-190)."""
+def _lora_case(pkg, M, N, K, dtype, n_loras=1, rank=4):
+    lin, raw, b = _layer(pkg, Q.Q4_K, N, K)
+    g = torch.Generator(device="cpu").manual_seed(N + K + M)
+    loras = [(torch.randn(N, rank, generator=g).to(DEV) * 0.05, torch.randn(rank, K, generator=g).to(DEV) * 0.05, 0.8 - 0.3 * i, 2.0 + i)
+             for i in range(n_loras)]
+    lin.weight.patches = [([(s, ("lora", (up, down, alpha, None, None, None)), 1.0, None, None)], "w") for up, down, s, alpha in loras]
+    x = torch.randn(M, K, generator=g).to(DEV).to(dtype)
+    W = pkg.ops._plain(pkg.dequant.dequantize_tensor(lin.weight, dtype))   # GGMLTensor.clone() returns self (ops.py:64-68)
+    delta = [s * (alpha / rank) * (up @ down) for up, down, s, alpha in loras]
+    # what the reference computes (ops.py:184-190): W rounded to the activation dtype after every patch, then F.linear
+    Wref = W.clone()
+    for d in delta:
+        Wref += d.to(dtype)
+    bias = torch.from_numpy(b).to(DEV)
+    ref = torch.nn.functional.linear(x.double(), Wref.double(), bias.to(dtype).double())
+    # the unrounded ideal
+    ideal = torch.nn.functional.linear(x.double(), W.double() + sum(delta).double(), bias.to(dtype).double())
+    return lin, x, ref, ideal
+
+
+def _rel(a, b):
+    return float((a.double() - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("M,N,K,dtype,n_loras", [(6, 64, 512, torch.bfloat16, 1), (6, 64, 512, torch.float16, 2),
+                                                (300, 264, 1024, torch.bfloat16, 1), (300, 264, 1024, torch.float16, 3)])
+def test_lora_on_packed_weight_runs_as_side_gemms(pkg, M, N, K, dtype, n_loras):
+    """LoRA-only patch lists are served by the packed-weight Linear plus rank-r side GEMMs.
+    Parity budget: the side-GEMM result must be (a) within 3e-3 (fp16) / 1e-2 (bf16) relative Frobenius of the reference's
+    dequant + calculate_weight + F.linear arithmetic and (b) no further from the unrounded ideal than 1.5x the reference is
+    (the reference additionally rounds W + delta to the activation dtype)."""
+    lin, x, ref, ideal = _lora_case(pkg, M, N, K, dtype, n_loras)
+    assert lin._lora_terms(x.device), "LoRA-only patch list must be recognised"
+    y = lin(x)
+    assert type(y) is torch.Tensor and y.dtype == dtype
+    budget = 3e-3 if dtype == torch.float16 else 1e-2
+    assert _rel(y, ref) <= budget
+    ref_rounded = ref.to(dtype)          # the reference's own output rounding
+    assert _rel(y, ideal) <= 1.5 * _rel(ref_rounded, ideal) + 1e-4
+    # knob off -> the reference's two-step arithmetic
+    lin.lora_side_gemm = False
+    try:
+        y2 = lin(x)
+    finally:
+        del lin.lora_side_gemm
+    assert _rel(y2, ref) <= (2e-3 if dtype == torch.float16 else 6e-3)
+    lin.weight.patches = []
+    assert lin._lora_terms(x.device) == []
+
+
+def test_non_lora_patch_takes_two_step_route(pkg):
+    """Anything calculate_weight-specific (diff patches, strength_model, offsets ...) keeps the reference route
+    (ops.py:171-190): dequant + comfy.lora.calculate_weight + F.linear."""
     lin, raw, _ = _layer(pkg, Q.Q4_K, 64, 512, bias=False)
-    up = torch.randn(64, 4, device=DEV) * 0.05
-    down = torch.randn(4, 512, device=DEV) * 0.05
-    lin.weight.patches = [([(0.8, ("lora", (up, down, 2.0, None, None, None)), 1.0, None, None)], "w")]
+    diff = torch.randn(64, 512, device=DEV) * 0.01
+    lin.weight.patches = [([(0.5, ("diff", (diff,)), 1.0, None, None)], "w")]
+    assert lin._lora_terms(torch.device(DEV)) is None
     x = torch.randn(6, 512, device=DEV, dtype=torch.bfloat16)
     y = lin(x)
-    W = pkg.dequant.dequantize_tensor(lin.weight, torch.bfloat16).float()
-    Wp = (W.to(torch.bfloat16) + (0.8 * (2.0 / 4) * (up @ down)).to(torch.bfloat16)).float()
-    ref = torch.nn.functional.linear(x.float(), Wp)
-    assert rel_fro(y.float().cpu().numpy(), ref.cpu().numpy()) <= 3e-3
-    lin.weight.patches = []
-    y0 = lin(x)
-    assert rel_fro(y0.float().cpu().numpy(), torch.nn.functional.linear(x.float(), W).cpu().numpy()) <= 2e-3
+    W = pkg.ops._plain(pkg.dequant.dequantize_tensor(lin.weight, torch.bfloat16))
+    ref = torch.nn.functional.linear(x.double(), (W + (0.5 * diff).to(torch.bfloat16)).double())
+    assert _rel(y, ref) <= 6e-3
+    up, down = torch.randn(64, 4, device=DEV), torch.randn(4, 512, device=DEV)
+    lin.weight.patches = [([(0.5, ("lora", (up, down, None, None, None, None)), 0.9, None, None)], "w")]   # strength_model != 1
+    assert lin._lora_terms(torch.device(DEV)) is None
+    lin.weight.patches = [([(0.5, ("lora", (up, down, None, None, torch.ones(64, device=DEV), None)), 1.0, None, None)], "w")]  # DoRA
+    assert lin._lora_terms(torch.device(DEV)) is None
 
 
 def test_embedding_row_gather_equals_reference_semantics(pkg):

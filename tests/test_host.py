@@ -201,3 +201,26 @@ def test_surface_matches_reference(pkg):
               "forward_comfy_cast_weights", "forward_ggml_cast_weights"):
         assert hasattr(pkg.ops.GGMLLayer, m)
     assert pkg.ops.GGMLLayer.comfy_cast_weights is True and pkg.ops.GGMLLayer.dequant_dtype is None
+
+
+def test_lora_side_terms_recognises_only_plain_lora(pkg):
+    """Host logic of the LoRA side-GEMM route: only (strength, ("lora", (up, down, alpha, None, None,
+    None)), 1.0, None, None) entries qualify; everything else must fall back to calculate_weight."""
+    f = pkg.ops.lora_side_terms
+    up, down = torch.ones(8, 2), torch.ones(2, 16)
+    terms = f([(0.5, ("lora", (up, down, 4.0, None, None, None)), 1.0, None, None), (1.0, ("lora", (up, down, None)), 1.0)])
+    assert [t[0] for t in terms] == [0.5 * 4.0 / 2, 1.0] and terms[0][1] is up and terms[0][2] is down
+    assert f([]) == []
+    assert f([(0.5, ("diff", (up,)), 1.0, None, None)]) is None
+    assert f([(0.5, up, 1.0, None, None)]) is None                                        # bare tensor = diff
+    assert f([(0.5, ("lora", (up, down, 4.0, None, None, None)), 0.7, None, None)]) is None      # strength_model
+    assert f([(0.5, ("lora", (up, down, 4.0, None, None, None)), 1.0, (0, 0, 4), None)]) is None  # offset
+    assert f([(0.5, ("lora", (up, down, 4.0, None, None, None)), 1.0, None, lambda w: w)]) is None
+    assert f([(0.5, ("lora", (up, down, 4.0, torch.ones(2, 2), None, None)), 1.0, None, None)]) is None   # LoCon mid
+    assert f([(0.5, ("lora", (up, down, 4.0, None, torch.ones(8), None)), 1.0, None, None)]) is None     # DoRA
+    assert f([(0.5, ("lora", (up, torch.ones(3, 16), 4.0, None, None, None)), 1.0, None, None)]) is None   # rank mismatch
+
+    class LoRAAdapter:                      # newer ComfyUI wraps the same tuple in an adapter object
+        def __init__(self, weights):
+            self.weights = weights
+    assert f([(1.0, LoRAAdapter((up, down, 2.0, None, None, None)), 1.0, None, None)])[0][0] == 1.0

@@ -19,10 +19,28 @@ from oracle import torch_chain  # noqa: E402
 SHAPES = [(3072, 3072), (9216, 3072), (12288, 3072), (3072, 12288), (18432, 3072), (21504, 3072), (3072, 15360)]
 
 
+GRAPH = False
+
+
 def timeit(fn, iters=10, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if GRAPH:   # kernel time without the Python / launch overhead: replay a captured batch of calls
+        per = 8
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(per):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (iters * per)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(iters):
@@ -38,15 +56,24 @@ def main():
     ap.add_argument("--M", type=int, nargs="+", default=[4608])
     ap.add_argument("--shapes", type=int, nargs="*", default=None, help="indices into SHAPES")
     ap.add_argument("--routes", nargs="*", default=["fused", "dq_mma", "k1_cublas", "cublas", "ref_chain"])
+    ap.add_argument("--nk", type=int, nargs="*", default=None, help="explicit N K pairs (flat list) instead of the Flux shapes")
     ap.add_argument("--copies", type=int, default=4)
     ap.add_argument("--variant", type=int, default=2, help="GEMM kernel: 2 = persistent pair (dense) + pair (fused), 1 = CTA pair, 0 = single CTA")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays (kernel time only)")
+    ap.add_argument("--no-splitk", action="store_true")
     args = ap.parse_args()
+    global GRAPH
+    GRAPH = args.graph
     ops, dq, lib = ge._sub("ops"), ge._sub("dequant"), ge._sub("_lib")
     dev = torch.device("cuda:0")
     lib.lib().ggufb200_set_tuning(2, args.variant)
+    if args.no_splitk:
+        lib.lib().ggufb200_set_tuning(6, 0)
     qt = gguf.GGMLQuantizationType[args.qtype]
     bs, ts = gguf.GGML_QUANT_SIZES[qt]
     shapes = SHAPES if not args.shapes else [SHAPES[i] for i in args.shapes]
+    if args.nk:
+        shapes = list(zip(args.nk[0::2], args.nk[1::2]))
     for (N, K) in shapes:
         ws = []
         for c in range(args.copies):
