@@ -49,7 +49,7 @@ static bool auto_prefers_fused(int type, long long M, long long N, long long K)
     if (!gemm_fused_supported(type) || (K % 64) != 0) return false;
     if (g_auto_fused) return true;
     if (M > 1024) return false;
-    if (g_gemm_variant >= 1) {   // split-K: all SM pairs dequantise in parallel (measured: profiles/r01_bench_linear_smallm.log)
+    if (g_gemm_variant >= 1) {   // split-K: all SM pairs dequantise in parallel (measured: profiles/r01_bench_linear_graph_m512_m64.log)
         const int splits = gemm2_fused_splits(M, N, K);
         if (splits >= 4 || (splits >= 2 && K >= 2 * N)) return true;
         if (splits >= 2) return false;
@@ -201,9 +201,10 @@ size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K,
 {
     if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0) return 0;
     const size_t dense = (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
-    const size_t splitk = (g_gemm_variant >= 1 && gemm_fused_supported(ggml_type) && gemm2_fused_splits(M, N, K) > 1) ? (size_t)M * (size_t)N * 4 : 0;
+    const size_t splitk = (g_gemm_variant >= 1 && gemm_fused_supported(ggml_type) && gemm2_fused_splits(M, N, K) > 1)
+                              ? (size_t)gemm2_fused_splits(M, N, K) * (size_t)M * (size_t)N * 4 : 0;
     if (algo == GGUFB200_ALGO_DEQUANT_MMA) return dense;
-    if (algo == GGUFB200_ALGO_FUSED_MMA) return splitk;          // fp32 accumulation buffer of the split-K fused kernel
+    if (algo == GGUFB200_ALGO_FUSED_MMA) return splitk;          // fp32 partial-result slices of the split-K fused kernel
     if (algo == GGUFB200_ALGO_AUTO && M > gemv_max_m()) return auto_prefers_fused(ggml_type, M, N, K) ? splitk : dense;
     return 0;
 }

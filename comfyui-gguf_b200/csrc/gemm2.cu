@@ -58,7 +58,7 @@ struct Gemm2Params {
     int tiles_m;
     int n_tiles;       // tiles_m * tiles_n
     int kb_per_split;  // k-blocks per split (a multiple of 4); == K/64 when the K loop is not split
-    float *partial;    // split-K: fp32 [M, N] accumulation buffer (zeroed by the host), else nullptr
+    float *partial;    // split-K: fp32 [splits, M, N] partial results (one slice per K range), else nullptr
     int splits;        // host side only
 };
 
@@ -288,8 +288,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             g2_tmem_ld32(taddr0 + c0, r);
             g2_tmem_ld_wait();
             if (p.partial) {
-                // split-K: add this pair's fp32 partial tile into the shared accumulation buffer (bias / cast happen in the
-                // finalize kernel).  Same transpose trick, 128-byte rows: eight lanes cover one row with red.global.add.v4.f32.
+                // split-K: store this pair's fp32 partial tile into slice `split` of the workspace (bias / cast / the sum over
+                // slices in a FIXED order happen in the finalize kernel, so results are run-to-run reproducible -- no atomics).
+                // Same transpose trick, 128-byte rows: eight lanes cover one row with st.global.v4.f32.
                 constexpr int PITCH32 = 144;
                 const uint32_t stage32 = smem_u32(tiles) + (uint32_t)warp * (32 * PITCH32);
 #pragma unroll
@@ -304,7 +305,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const long long m = m_base + row;
                     const long long n = n0 + c0 + part * 4;
                     if (m < p.M && n < p.N)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.partial + m * p.N + n), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        *reinterpret_cast<float4 *>(p.partial + ((long long)split * p.M + m) * p.N + n) = v;
                 }
                 __syncwarp();
                 continue;
@@ -373,16 +374,21 @@ static int g2_pick_accs(long long M, long long N, bool fused = false)
     return eff(2) + 0.10 >= eff(1) ? 2 : 1;
 }
 
-// split-K finalize: Y = act(P + bias)
+// split-K finalize: Y = act(sum_s P[s] + bias), slices added in ascending order
 template <int ACT>
-__global__ void __launch_bounds__(256) g2_finalize_kernel(const float *__restrict__ P, const void *__restrict__ bias, int bias_dtype,
+__global__ void __launch_bounds__(256) g2_finalize_kernel(const float *__restrict__ P, int splits, const void *__restrict__ bias, int bias_dtype,
                                                           uint8_t *__restrict__ Y, long long M, long long N, long long ldy)
 {
     const long long n8 = N / 8;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < M * n8; i += (long long)gridDim.x * 256) {
         const long long m = i / n8, n = (i % n8) * 8;
-        const float4 a = *reinterpret_cast<const float4 *>(P + m * N + n), b = *reinterpret_cast<const float4 *>(P + m * N + n + 4);
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sp = 0; sp < splits; ++sp) {
+            const float *src = P + ((long long)sp * M + m) * N + n;
+            const float4 a = *reinterpret_cast<const float4 *>(src), b = *reinterpret_cast<const float4 *>(src + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
         if (bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += g2_bias<ACT>(bias, bias_dtype, n + j);
@@ -398,17 +404,22 @@ int g_fused_splitk = 1;   // ggufb200_set_tuning(6, v)
 
 // Tiling of the fused kernel: ACCS (256 or 512 activation rows per pair) and the split-K factor.
 // Short activations give too few (256*ACCS x 256) tiles for the 74 SM pairs, so the K loop is cut into S ranges of whole
-// 256-wide spans, each handled by its own pair, and the fp32 partial tiles are summed in the caller's workspace.  The fused
+// 256-wide spans, each handled by its own pair, which stores its fp32 partial tile into its own slice of the caller's
+// workspace ([S, M, N] fp32; bounded so the slices stay L2-resident until the finalize kernel sums them).  The fused
 // kernel is bound by its dequant producers, and every M tile dequantises its W tile again, so when splitting is possible
 // the tallest tile (ACCS = 2) wins: each packed byte is then read and dequantised once per 512 activation rows.
 struct G2Plan {
     int accs, splits;
 };
 
-static G2Plan g2_fused_plan(long long M, long long N, long long K, bool can_split)
+constexpr size_t kG2SplitWsCap = 64u << 20;   // half of the 126 MB L2
+
+static G2Plan g2_fused_plan(long long M, long long N, long long K, size_t ws_bytes)
 {
     G2Plan plan{g2_pick_accs(M, N, true), 1};
-    if (!can_split || !g_fused_splitk || K % kG2Span != 0) return plan;
+    const size_t slice = (size_t)M * (size_t)N * 4;
+    if (ws_bytes > kG2SplitWsCap) ws_bytes = kG2SplitWsCap;
+    if (slice == 0 || ws_bytes < 2 * slice || !g_fused_splitk || K % kG2Span != 0) return plan;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -417,19 +428,20 @@ static G2Plan g2_fused_plan(long long M, long long N, long long K, bool can_spli
     auto tiles = [&](int accs) { return ((M + 256 * accs - 1) / (256 * accs)) * tiles_n; };
     if (M > 256 && tiles(2) * 2 <= pairs) plan.accs = 2;
     const long long t = tiles(plan.accs);
-    if (t * 2 > pairs) return plan;
+    if (t * 2 > pairs) return plan;   // (accs unchanged in this case)
     const long long spans = K / kG2Span;
     long long s = pairs / t;
     if (s > spans) s = spans;
     if (s > 16) s = 16;
-    if (s < 2) return plan;
+    if (s > (long long)(ws_bytes / slice)) s = (long long)(ws_bytes / slice);
+    if (s < 2) return G2Plan{g2_pick_accs(M, N, true), 1};
     const long long per = (spans + s - 1) / s;
     plan.splits = (int)((spans + per - 1) / per);
     return plan;
 }
 
 // split-K factor the fused route would use given a workspace (ggufb200_linear_workspace / AUTO routing)
-int gemm2_fused_splits(long long M, long long N, long long K) { return g2_fused_plan(M, N, K, true).splits; }
+int gemm2_fused_splits(long long M, long long N, long long K) { return g2_fused_plan(M, N, K, kG2SplitWsCap).splits; }
 
 template <class Q, int MATH, int ACT, int ACCS, bool STAGED = false>
 static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2Params &p, cudaStream_t st)
@@ -476,17 +488,16 @@ template <class Q, int ACT>
 static int g2_fused_act(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
                         void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    // split-K needs the fp32 [M, N] accumulation buffer from the caller's workspace
-    const bool ws_ok = ws && ws_bytes >= (size_t)M * (size_t)N * 4 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
-    const G2Plan plan = g2_fused_plan(M, N, K, ws_ok);
+    // split-K needs room for the fp32 [splits, M, N] partial results in the caller's workspace
+    const bool ws_ok = ws && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
+    const G2Plan plan = g2_fused_plan(M, N, K, ws_ok ? ws_bytes : 0);
     if (plan.splits <= 1) return g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, nullptr, plan, st);
     float *P = reinterpret_cast<float *>(ws);
-    if (cudaMemsetAsync(P, 0, (size_t)M * (size_t)N * 4, st) != cudaSuccess) return GGUFB200_E_CUDA;
     int rc = g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, nullptr, 0, Y, ldy, P, plan, st);
     if (rc != GGUFB200_OK) return rc;
     long long work = M * (N / 8);
     unsigned grid = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
-    g2_finalize_kernel<ACT><<<grid, 256, 0, st>>>(P, bias, bias_dtype, reinterpret_cast<uint8_t *>(Y), M, N, ldy);
+    g2_finalize_kernel<ACT><<<grid, 256, 0, st>>>(P, plan.splits, bias, bias_dtype, reinterpret_cast<uint8_t *>(Y), M, N, ldy);
     return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 

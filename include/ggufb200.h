@@ -113,8 +113,9 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
  *   bias        NULL or N values of bias_dtype (0/1/2)
  *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0).  A W_packed that is
  *               not 16-byte aligned is always served by GGUFB200_ALGO_DEQUANT_MMA and needs that algo's workspace.
- *               GGUFB200_ALGO_FUSED_MMA with few output tiles (short M) cuts K across SM pairs and accumulates fp32
- *               partial tiles in the workspace (M*N*4 bytes); without it the kernel runs unsplit.  The size reported
+ *               GGUFB200_ALGO_FUSED_MMA with few output tiles (short M) cuts K into S ranges across SM pairs and keeps
+ *               the fp32 partial results in the workspace (S*M*N*4 bytes, summed in a fixed order: reproducible);
+ *               with less room it uses fewer ranges, with none it runs unsplit.  The size reported
  *               for GGUFB200_ALGO_AUTO assumes math_dtype == fp16 (the reference default); with another math dtype
  *               query and pass GGUFB200_ALGO_DEQUANT_MMA.
  *   algo        GGUFB200_ALGO_*

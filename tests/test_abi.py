@@ -74,7 +74,7 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
 
 def test_tuning_keys_and_gemm_validation_without_gpu(pkg):
     L = pkg.lib.lib()
-    for key, value in ((0, 4), (1, 1), (2, 2), (3, 0), (4, 1), (5, 1)):
+    for key, value in ((0, 4), (1, 1), (2, 2), (3, 0), (4, 1), (5, 1), (6, 1)):
         assert L.ggufb200_set_tuning(key, value) == 0
     assert L.ggufb200_set_tuning(99, 1) == -8                      # unknown knob
     L.ggufb200_set_tuning(0, 0)
@@ -87,5 +87,17 @@ def test_tuning_keys_and_gemm_validation_without_gpu(pkg):
     assert L.ggufb200_gemm(p16, 8, 64, 64, p16, 0, 64, 1, None, 0, p16, 8, None) == 0   # M == 0 is a no-op
     # ggufb200_linear: an unaligned packed weight needs the dequant+GEMM workspace
     assert L.ggufb200_linear(int(Q.Q4_K), p16 + 2, 8, 256, p16, 4, 256, 1, 0, None, 0, p16, 8, None, 0, 0, None) == -3
+    # workspace contract (no GPU needed): dequant+GEMM wants the dense weight, the fused kernel its split-K accumulation buffer
+    q4k = int(Q.Q4_K)
+    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 3) == 3072 * 3072 * 2      # ALGO_DEQUANT_MMA
+    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 2) == 0                    # FUSED, enough tiles
+    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 2) == 16 * 64 * 512 * 4       # FUSED, split-K: 16 slices
+    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 0) == 16 * 64 * 512 * 4       # AUTO picks split-K fused
+    assert L.ggufb200_linear_workspace(q4k, 512, 3072, 12288, 1, 2) == 6 * 512 * 3072 * 4   # 12 tiles of 512x256 -> 6 ranges
+    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 0) == 3072 * 3072 * 2      # AUTO picks dequant+GEMM
+    assert L.ggufb200_linear_workspace(q4k, 4, 3072, 3072, 1, 0) == 0                       # GEMV
+    L.ggufb200_set_tuning(6, 0)
+    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 2) == 0
+    L.ggufb200_set_tuning(6, 1)
     # row gather: K must be a multiple of the block size
     assert L.ggufb200_dequant_rows(int(Q.Q4_K), p16, 4, 100, p16, 1, p16, 0, 0, None) == -4

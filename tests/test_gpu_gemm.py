@@ -63,6 +63,58 @@ def test_fused_gemm_all_types(pkg, qt, dt):
     assert rel_fro(y.float().cpu().numpy(), _ref(x, W, b).float().cpu().numpy()) <= TOL
 
 
+@pytest.mark.parametrize("qt", [Q.Q4_K, Q.Q8_0, Q.Q6_K, Q.Q5_0], ids=lambda q: q.name)
+@pytest.mark.parametrize("M,N,K", [(64, 512, 4096), (300, 264, 2048), (513, 520, 1280), (1000, 256, 5120), (24, 1032, 768)])
+def test_fused_gemm_split_k(pkg, gemm_variant, qt, M, N, K):
+    """Short activations: the fused kernel cuts K into ranges of whole 256-wide spans, one SM pair per (tile, range), and
+    keeps fp32 partial tiles in the workspace and sums them in a fixed order (bit-reproducible).  Checked against the reference arithmetic and against the unsplit kernel
+    (same tiles, no workspace): the two may differ only by fp32 summation order."""
+    L = pkg.lib.lib()
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    raw = oracle.random_blocks(int(qt), N * K // bs, seed=int(qt) + K, scale=0.02).reshape(N, K // bs * ts)
+    w = pkg.ops.GGMLTensor(torch.from_numpy(raw).to(DEV), tensor_type=qt, tensor_shape=torch.Size((N, K)))
+    W = pkg.dequant.dequantize_tensor(w, torch.bfloat16)
+    x = torch.randn(M, K, device=DEV, dtype=torch.bfloat16)
+    b = torch.randn(N, device=DEV) * 0.1
+    variant, _staged = gemm_variant
+    L.ggufb200_set_tuning(6, 1)
+    need = L.ggufb200_linear_workspace(int(qt), M, N, K, 1, pkg.lib.ALGO_FUSED_MMA)
+    if variant == 0:
+        assert need == 0                    # the single-CTA kernel has no split-K
+    else:
+        assert need % (M * N * 4) == 0 and need >= 2 * M * N * 4, "these shapes leave SM pairs idle without split-K"
+    y = pkg.ops.linear_packed(x, w, b, None, pkg.lib.ALGO_FUSED_MMA)
+    assert torch.equal(y, pkg.ops.linear_packed(x, w, b, None, pkg.lib.ALGO_FUSED_MMA)), "split-K must be reproducible"
+    L.ggufb200_set_tuning(6, 0)
+    try:
+        assert L.ggufb200_linear_workspace(int(qt), M, N, K, 1, pkg.lib.ALGO_FUSED_MMA) == 0
+        y1 = pkg.ops.linear_packed(x, w, b, None, pkg.lib.ALGO_FUSED_MMA)
+    finally:
+        L.ggufb200_set_tuning(6, 1)
+    ref = _ref(x, W, b).float().cpu().numpy()
+    assert rel_fro(y.float().cpu().numpy(), ref) <= TOL
+    assert rel_fro(y1.float().cpu().numpy(), ref) <= TOL
+    assert rel_fro(y.float().cpu().numpy(), y1.float().cpu().numpy()) <= 2e-3   # bf16 output rounding of two fp32 orders
+    ya = pkg.ops.linear_packed(x, w, None, None, pkg.lib.ALGO_AUTO)
+    assert rel_fro(ya.float().cpu().numpy(), _ref(x, W, None).float().cpu().numpy()) <= TOL
+
+
+def test_fused_split_k_without_workspace_runs_unsplit(pkg):
+    """The C ABI never allocates: FUSED_MMA with a NULL workspace must still be correct (one pair per tile)."""
+    qt, M, N, K = Q.Q4_K, 64, 512, 4096
+    raw = oracle.random_blocks(int(qt), N * K // 256, seed=9, scale=0.02).reshape(N, K // 256 * 144)
+    w = torch.from_numpy(raw).to(DEV)
+    x = torch.randn(M, K, device=DEV, dtype=torch.float16)
+    y = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    L = pkg.lib.lib()
+    rc = L.ggufb200_linear(int(qt), w.data_ptr(), N, K, x.data_ptr(), M, K, 0, 0, None, 0, y.data_ptr(), N, None, 0,
+                           pkg.lib.ALGO_FUSED_MMA, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    gw = pkg.ops.GGMLTensor(w, tensor_type=qt, tensor_shape=torch.Size((N, K)))
+    W = pkg.dequant.dequantize_tensor(gw, torch.float16)
+    assert rel_fro(y.float().cpu().numpy(), _ref(x, W, None).float().cpu().numpy()) <= TOL
+
+
 @pytest.mark.parametrize("route", ["fused", "dequant+mma", "auto"])
 def test_sd35_shape_q8_0_unaligned_rows(pkg, route):
     """SD3.5-large hidden size 2432: Q8_0 rows are 2584 bytes (not a multiple of 16), so no tensor map over the packed bytes
