@@ -321,14 +321,19 @@ template <int ACT> struct Fast16<Block<T_Q4_K>, ACT> {
         uint32_t dm_bits = h.x;
         const __half2 DM = __hmul2_rn(*reinterpret_cast<__half2 *>(&dm_bits), scm);
         const __half2 D2 = __low2half2(DM), M2 = __high2half2(DM);
-        const int nib = 4 * (sb & 1);                                         // odd sub-blocks live in the high nibbles
+        // odd sub-blocks live in the high nibbles.  Instead of shifting them down, keep q << 4 in place and build the fp16
+        // pattern 0x5400 | (q << 4) = 64 + q (ulp 1/16 at 64) -- the low-nibble case is the usual 0x6400 | q = 1024 + q
+        const bool hi = (sb & 1) != 0;
+        const uint32_t mask = hi ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
+        const uint32_t magic = hi ? 0x54545454u : 0x64646464u;
+        const __half2 kmagic = __half2half2(__ushort_as_half((unsigned short)(hi ? 0x5400u : 0x6400u)));
         const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t v = (w[i] >> nib) & 0x0F0F0F0Fu;
-            uint32_t l = prmt(v, 0x64646464u, 0x4140u), u = prmt(v, 0x64646464u, 0x4342u);
-            __half2 lo = __hsub2_rn(*reinterpret_cast<__half2 *>(&l), k1024);
-            __half2 up = __hsub2_rn(*reinterpret_cast<__half2 *>(&u), k1024);
+            const uint32_t v = w[i] & mask;
+            uint32_t l = prmt(v, magic, 0x4140u), u = prmt(v, magic, 0x4342u);
+            __half2 lo = __hsub2_rn(*reinterpret_cast<__half2 *>(&l), kmagic);
+            __half2 up = __hsub2_rn(*reinterpret_cast<__half2 *>(&u), kmagic);
             lo = __hsub2_rn(__hmul2_rn(D2, lo), M2);
             up = __hsub2_rn(__hmul2_rn(D2, up), M2);
             out[2 * i] = pack_h2_to_act<ACT>(lo);

@@ -198,4 +198,49 @@ template <int OUT, int MATH> __device__ __forceinline__ uint32_t pack16(typename
     }
 }
 
+// Index of the CUDA current device for the per-device caches below, -1 when no device is visible.
+inline int device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return -1;
+    }
+    return dev;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE property of a kernel: raise it once on every device the
+// process launches on (a process-wide "done" flag would leave the second GPU of a multi-GPU host at the 48 KB default).
+template <class Kernel> inline bool ensure_dynamic_smem(Kernel kern, int bytes, unsigned char (&done)[64])
+{
+    const int dev = device_slot();
+    if (dev < 0) return false;
+    if (!done[dev]) {
+        if (bytes > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+        done[dev] = 1;
+    }
+    return true;
+}
+
+// SM count of the current device, queried once per device (the attribute call is a driver round trip that showed up in the
+// host cost of short-activation Linears).  148 when no device is visible (ABI tests on a CPU-only box).
+inline int sm_count()
+{
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return 148;
+    }
+    if (cache[dev] == 0) {
+        int sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+            cudaGetLastError();
+            sms = 148;
+        }
+        cache[dev] = sms;
+    }
+    return cache[dev];
+}
+
 }  // namespace ggufb200

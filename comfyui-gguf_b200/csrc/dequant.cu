@@ -214,18 +214,6 @@ __global__ void unpack_int_kernel(const uint8_t *__restrict__ src, long long n_b
 }
 
 // ------------------------------------------------------------------ host-side dispatch
-static int sm_count()
-{
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 template <class Q, int MATH, int OUT> static int launch_dequant(const void *packed, long long n_blocks, void *out, cudaStream_t st)
 {
     constexpr int STAGES = 3;
@@ -234,9 +222,11 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
     constexpr int SLOT_BYTES = TILE_BLOCKS * Q::TS + 16;
     constexpr int SMEM = 128 + STAGES * SLOT_BYTES + 2 * TILE_ELEMS * OutT<OUT>::bytes;
     auto kern = dequant_kernel<Q, MATH, OUT, STAGES, TILE_ELEMS>;
-    static int resident = 0;   // CTAs of this instantiation that fit on one SM
+    static unsigned char smem_set[64] = {};
+    static int resident_on[64] = {};   // CTAs of this instantiation that fit on one SM, per device
+    if (!ensure_dynamic_smem(kern, SMEM, smem_set)) return GGUFB200_E_CUDA;
+    int &resident = resident_on[device_slot()];
     if (resident == 0) {
-        if (SMEM > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, SMEM) != cudaSuccess || n < 1) n = 1;
         resident = n > 4 ? 4 : n;

@@ -319,9 +319,7 @@ static bool make_map(CUtensorMap *tm, const void *base, long long rows, long lon
 
 static int pick_bn(long long M, long long N)
 {
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     long long tm = (M + kBM - 1) / kBM;
     auto eff = [&](int bn) {
         long long tiles = tm * ((N + bn - 1) / bn);
@@ -337,11 +335,8 @@ static int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gem
 {
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_kernel<Q, MATH, ACT, BN>;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GGUFB200_E_CUDA;
-        attr = true;
-    }
+    static unsigned char attr[64] = {};
+    if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
     GemmParams q = p;
     q.tiles_m = (int)((p.M + kBM - 1) / kBM);
     long long tiles_n = (p.N + BN - 1) / BN;

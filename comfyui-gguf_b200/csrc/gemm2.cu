@@ -358,9 +358,7 @@ int g_fused_staged = 1;   // ggufb200_set_tuning(4, v): stage packed rows throug
 // wave of 512-row tiles would leave too many SM pairs idle
 static int g2_pick_accs(long long M, long long N, bool fused = false)
 {
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const long long pairs = sms / 2;
     auto eff = [&](int accs) {
         long long tiles = ((M + 256 * accs - 1) / (256 * accs)) * ((N + kG2BN - 1) / kG2BN);
@@ -420,9 +418,7 @@ static G2Plan g2_fused_plan(long long M, long long N, long long K, size_t ws_byt
     const size_t slice = (size_t)M * (size_t)N * 4;
     if (ws_bytes > kG2SplitWsCap) ws_bytes = kG2SplitWsCap;
     if (slice == 0 || ws_bytes < 2 * slice || !g_fused_splitk || K % kG2Span != 0) return plan;
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const long long pairs = sms / 2;
     const long long tiles_n = (N + kG2BN - 1) / kG2BN;
     auto tiles = [&](int accs) { return ((M + 256 * accs - 1) / (256 * accs)) * tiles_n; };
@@ -448,11 +444,8 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
 {
     using Cfg = Gemm2Cfg<ACCS, STAGED ? PackedSeg<Q>::value : 0>;
     auto kern = gemm2_kernel<Q, MATH, ACT, ACCS, STAGED>;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return GGUFB200_E_CUDA;
-        attr = true;
-    }
+    static unsigned char attr[64] = {};
+    if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
     Gemm2Params q = p;
     q.tiles_m = (int)((p.M + 256 * ACCS - 1) / (256 * ACCS));
     const long long tiles_n = (p.N + kG2BN - 1) / kG2BN;

@@ -197,15 +197,9 @@ static int g3_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, Gemm3Params
 {
     constexpr int kG3Smem = Gemm3Cfg<BN>::SMEM;
     auto kern = gemm3_kernel<ACT, BN>;
-    static bool attr = false;
-    static int sms = 148;
-    if (!attr) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG3Smem) != cudaSuccess) return GGUFB200_E_CUDA;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr = true;
-    }
+    static unsigned char attr[64] = {};
+    if (!ensure_dynamic_smem(kern, kG3Smem, attr)) return GGUFB200_E_CUDA;
+    const int sms = sm_count();
     p.tiles_m = (int)((p.M + 255) / 256);
     p.n_tiles = p.tiles_m * (int)((p.N + BN - 1) / BN);
     int pairs = sms / 2;
@@ -229,9 +223,7 @@ int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw,
                          const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
     if (K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const long long tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
     const bool narrow = tiles256 <= sms / 4;       // far fewer 256-wide tiles than SM pairs: halve the tile width
     CUtensorMap tmA, tmB;

@@ -146,21 +146,33 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_mma_kernel(const uint8_t *_
             const int e0 = (int)(k % Q::BS);
             if constexpr (MATH == kF16 && Fast16<Q, ACT>::available) {
                 // hand-scheduled producers (one 16-byte header load + one 16-byte quant load per 16 elements)
+                // interior tiles / spans (warp-uniform test) skip the per-register edge masking
+                const bool interior = n0 + 16 <= N && span * 128 + 128 <= K;
 #pragma unroll
                 for (int hseg = 0; hseg < 2; ++hseg) {
                     uint32_t a[8], b[8];
                     Fast16<Q, ACT>::run(b0p, e0 + hseg * 16, a);
                     Fast16<Q, ACT>::run(b1p, e0 + hseg * 16, b);
+                    if (interior) {
 #pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        uint4 xv = make_uint4(0, 0, 0, 0);
-                        if (xrow_ok && kin) xv = *reinterpret_cast<const uint4 *>(xrow + (k + hseg * 16 + t * 8) * 2);
-                        const uint32_t a0 = (ok0 && kin) ? a[4 * t] : 0u, a1 = (ok0 && kin) ? a[4 * t + 1] : 0u;
-                        const uint32_t a2 = (ok0 && kin) ? a[4 * t + 2] : 0u, a3 = (ok0 && kin) ? a[4 * t + 3] : 0u;
-                        const uint32_t c0 = (ok1 && kin) ? b[4 * t] : 0u, c1 = (ok1 && kin) ? b[4 * t + 1] : 0u;
-                        const uint32_t c2 = (ok1 && kin) ? b[4 * t + 2] : 0u, c3 = (ok1 && kin) ? b[4 * t + 3] : 0u;
-                        mma_16x8x16<ACT>(d, a0, c0, a1, c1, xv.x, xv.y);
-                        mma_16x8x16<ACT>(d, a2, c2, a3, c3, xv.z, xv.w);
+                        for (int t = 0; t < 2; ++t) {
+                            uint4 xv = make_uint4(0, 0, 0, 0);
+                            if (xrow_ok) xv = *reinterpret_cast<const uint4 *>(xrow + (k + hseg * 16 + t * 8) * 2);
+                            mma_16x8x16<ACT>(d, a[4 * t], b[4 * t], a[4 * t + 1], b[4 * t + 1], xv.x, xv.y);
+                            mma_16x8x16<ACT>(d, a[4 * t + 2], b[4 * t + 2], a[4 * t + 3], b[4 * t + 3], xv.z, xv.w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            uint4 xv = make_uint4(0, 0, 0, 0);
+                            if (xrow_ok && kin) xv = *reinterpret_cast<const uint4 *>(xrow + (k + hseg * 16 + t * 8) * 2);
+                            const uint32_t a0 = (ok0 && kin) ? a[4 * t] : 0u, a1 = (ok0 && kin) ? a[4 * t + 1] : 0u;
+                            const uint32_t a2 = (ok0 && kin) ? a[4 * t + 2] : 0u, a3 = (ok0 && kin) ? a[4 * t + 3] : 0u;
+                            const uint32_t c0 = (ok1 && kin) ? b[4 * t] : 0u, c1 = (ok1 && kin) ? b[4 * t + 1] : 0u;
+                            const uint32_t c2 = (ok1 && kin) ? b[4 * t + 2] : 0u, c3 = (ok1 && kin) ? b[4 * t + 3] : 0u;
+                            mma_16x8x16<ACT>(d, a0, c0, a1, c1, xv.x, xv.y);
+                            mma_16x8x16<ACT>(d, a2, c2, a3, c3, xv.z, xv.w);
+                        }
                     }
                 }
             } else {
@@ -251,9 +263,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_bf16w_kernel(const uint16_t
 
 static unsigned gemv_grid(long long N)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     long long blocks = (N + 7) / 8;
     long long cap = (long long)sms * 8;
     return (unsigned)(blocks < cap ? blocks : cap);
@@ -268,9 +278,7 @@ static int gemv_launch(const void *W, long long N, long long K, const void *X, l
     uint8_t *y = reinterpret_cast<uint8_t *>(Y);
     if (g_gemv_mma && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {   // the 16-byte header / quant loads need an aligned base
         long long tiles = (N + 15) / 16;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int sms = sm_count();
         long long cap = (long long)sms * 8;
         unsigned g = (unsigned)(tiles < cap ? tiles : cap);
         gemv_mma_kernel<Q, MATH, ACT><<<g, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);

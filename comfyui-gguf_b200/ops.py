@@ -97,52 +97,80 @@ def _plain(t):
     return t.as_subclass(torch.Tensor) if isinstance(t, GGMLTensor) else t
 
 
-def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
-    """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.
+# Raw-handle accessors: `torch.cuda.current_stream()` builds a Stream object through three layers of Python (~5 us per
+# call, more than the kernel launch it precedes); the private C entry points return the same values directly.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
 
-    x: CUDA fp16/bf16 [..., K]; weight: CUDA GGMLTensor (quantised type); bias: None or a CUDA tensor
-    (fp32 / fp16 / bf16, rounded to x.dtype inside the kernel exactly like ops.py:205-207 does)."""
-    qtype = weight.tensor_type
-    N, K = tuple(weight.tensor_shape)
-    if x.shape[-1] != K:
-        raise ValueError(f"linear_packed: input features {x.shape[-1]} != weight in_features {K}")
-    x2 = x.reshape(-1, K)
-    if x2.stride(-1) != 1 or (x2.stride(0) % 8) != 0 or (x2.data_ptr() % 16) != 0:
+
+def _current_stream_ptr(index):
+    if _raw_stream is not None:
+        return _raw_stream(index)
+    return torch.cuda.current_stream(index).cuda_stream
+
+
+def _is_current_device(index):
+    return index == (_raw_device() if _raw_device is not None else torch.cuda.current_device())
+
+
+_F16_CODE = _lib.F16
+
+
+def _launch_linear(x, wraw, qtype, N, K, bias, math, algo):
+    """The call itself.  x: CUDA fp16/bf16 [..., K]; wraw: PLAIN uint8 tensor holding the packed rows on x.device;
+    bias: PLAIN tensor on x.device or None.  Kept free of tensor-subclass traffic (every attribute read on a GGMLTensor
+    goes through __torch_function__) and of per-call object construction: for short activations the host side of this
+    function, not the GPU, bounds the layer."""
+    x2 = x if x.dim() == 2 else x.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.stride(0) & 7) or (x2.data_ptr() & 15):
         x2 = x2.contiguous()
     M = x2.shape[0]
-    y = torch.empty(M, N, dtype=x.dtype, device=x.device)
-    wraw = _plain(weight)
+    device = x.device
+    y = torch.empty((M, N), dtype=x.dtype, device=device)
     if not wraw.is_contiguous():
         wraw = wraw.contiguous()
     act = dtype_code(x.dtype)
     bias_ptr, bias_code = None, 0
     if bias is not None:
-        bias = _plain(bias)
         if not bias.is_contiguous():
             bias = bias.contiguous()
         bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
-    L = _lib.lib()
-    math = math_code(dequant_dtype, x.dtype)
-    if wraw.data_ptr() % 16 != 0:
+    w_ptr = wraw.data_ptr()
+    if w_ptr & 15:
         algo = _lib.ALGO_DEQUANT_MMA      # byte-offset view: only the standalone dequant stages arbitrary alignment
-    elif algo == _lib.ALGO_AUTO and M > GEMV_MAX_M and math != dtype_code(torch.float16):
+    elif algo == _lib.ALGO_AUTO and M > GEMV_MAX_M and math != _F16_CODE:
         algo = _lib.ALGO_DEQUANT_MMA      # the fused tensor-core producer is fp16-math only; size the workspace accordingly
-    ws, ws_ptr, ws_bytes = None, None, 0
+    L = _lib.lib()
     qcode = int(qtype)
-    need = L.ggufb200_linear_workspace(qcode, M, N, K, act, algo)
+    ws, ws_ptr = None, None
+    gemv = M <= GEMV_MAX_M and algo == _lib.ALGO_AUTO          # the small-M kernel needs no scratch: skip the query
+    need = 0 if gemv else L.ggufb200_linear_workspace(qcode, M, N, K, act, algo)
     if need:
-        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-        ws_ptr, ws_bytes = ws.data_ptr(), need
-    call = (qcode, wraw.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
-            ws_ptr, ws_bytes, algo)
-    if x.device.index == torch.cuda.current_device():     # the common case: skip the device-guard round trip
-        rc = L.ggufb200_linear(*call, torch.cuda.current_stream().cuda_stream)
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        ws_ptr = ws.data_ptr()
+    index = device.index
+    if _is_current_device(index):                     # the common case: no device-guard round trip
+        rc = L.ggufb200_linear(qcode, w_ptr, N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
+                               ws_ptr, need, algo, _current_stream_ptr(index))
     else:
-        with torch.cuda.device(x.device):
-            rc = L.ggufb200_linear(*call, torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(device):
+            rc = L.ggufb200_linear(qcode, w_ptr, N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
+                                   ws_ptr, need, algo, _current_stream_ptr(index))
     if rc:
         _lib.check(rc, f"ggufb200_linear({getattr(qtype, 'name', qtype)}, M={M}, N={N}, K={K})")
-    return y.reshape(*x.shape[:-1], N)
+    return y if x.dim() == 2 else y.reshape(*x.shape[:-1], N)
+
+
+def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
+    """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.
+
+    x: CUDA fp16/bf16 [..., K]; weight: CUDA GGMLTensor (quantised type); bias: None or a CUDA tensor
+    (fp32 / fp16 / bf16, rounded to x.dtype inside the kernel exactly like ops.py:205-207 does)."""
+    N, K = tuple(weight.tensor_shape)
+    if x.shape[-1] != K:
+        raise ValueError(f"linear_packed: input features {x.shape[-1]} != weight in_features {K}")
+    return _launch_linear(x, _plain(weight), weight.tensor_type, N, K, None if bias is None else _plain(bias),
+                          math_code(dequant_dtype, x.dtype), algo)
 
 
 def linear_dense(x, weight, bias=None):
@@ -369,19 +397,26 @@ class GGMLOps(comfy_ops.manual_cast):
             terms = self._lora_terms(input.device) if self._fused_ok(input) else None
             if terms is not None:
                 dev = input.device
-                w = self.weight if self.weight.device == dev else self.weight.to(dev)   # offloaded module: packed bytes H2D
+                w = self.weight
+                qtype, (N, K) = w.tensor_type, w.tensor_shape          # plain Python attributes: no subclass dispatch
+                wraw = w.as_subclass(torch.Tensor)
+                if wraw.device != dev:
+                    wraw = wraw.to(dev)                                # offloaded module: packed bytes H2D
                 b = self.bias
-                if b is not None and b.device != dev:
-                    b = b.to(dev)
-                M = input.numel() // input.shape[-1]
-                K = input.shape[-1]
-                if w.tensor_type == _Q.BF16 and M > GEMV_MAX_M:
-                    if input.dtype == torch.bfloat16 and K % 64 == 0:      # already dense: straight to the tensor-core GEMM
-                        dense = _plain(w).view(torch.bfloat16).view(w.tensor_shape[0], K)
-                        y = linear_dense(input, dense, b)
-                        return self._add_lora(y, input, terms) if terms else y
-                elif M <= GEMV_MAX_M or (K % 64 == 0 and w.tensor_shape[0] % 8 == 0):
-                    y = linear_packed(input, w, b, self.dequant_dtype)
+                if b is not None:
+                    b = _plain(b)
+                    if b.device != dev:
+                        b = b.to(dev)
+                M = input.numel() // K if input.shape[-1] == K else -1
+                y = None
+                if M < 0:
+                    pass                                               # feature mismatch: let F.linear raise the usual error
+                elif qtype == _Q.BF16 and M > GEMV_MAX_M:
+                    if input.dtype == torch.bfloat16 and K % 64 == 0:  # already dense: straight to the tensor-core GEMM
+                        y = linear_dense(input, wraw.view(torch.bfloat16).view(N, K), b)
+                elif M <= GEMV_MAX_M or (K % 64 == 0 and N % 8 == 0):
+                    y = _launch_linear(input, wraw, qtype, N, K, b, math_code(self.dequant_dtype, input.dtype), _lib.ALGO_AUTO)
+                if y is not None:
                     return self._add_lora(y, input, terms) if terms else y
             weight, bias = self.cast_bias_weight(input)
             return torch.nn.functional.linear(input, weight, bias)
