@@ -326,20 +326,16 @@ template <int ACT> struct Fast16<Block<T_Q4_K>, ACT> {
         const bool hi = (sb & 1) != 0;
         const uint32_t mask = hi ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
         const uint32_t magic = hi ? 0x54545454u : 0x64646464u;
-        // fp16(D*q) with q = pattern - 2^k (k = 10 or 6) as ONE fused multiply-add: D*pattern - 2^k*D is exact before the
-        // single rounding of the fma (2^k*D is an exact fp16 scaling, |D| << 64), so the result equals the reference's
-        // rounded product bit for bit and the separate "remove the magic number" subtraction disappears.
-        const __half2 kscale = __half2half2(__ushort_as_half((unsigned short)(hi ? 0xD400u : 0xE400u)));   // -64 / -1024
-        const __half2 negDk = __hmul2_rn(D2, kscale);
+        const __half2 kmagic = __half2half2(__ushort_as_half((unsigned short)(hi ? 0x5400u : 0x6400u)));
         const uint32_t w[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t v = w[i] & mask;
             uint32_t l = prmt(v, magic, 0x4140u), u = prmt(v, magic, 0x4342u);
-            __half2 lo = __hfma2(D2, *reinterpret_cast<__half2 *>(&l), negDk);
-            __half2 up = __hfma2(D2, *reinterpret_cast<__half2 *>(&u), negDk);
-            lo = __hsub2_rn(lo, M2);
-            up = __hsub2_rn(up, M2);
+            __half2 lo = __hsub2_rn(*reinterpret_cast<__half2 *>(&l), kmagic);
+            __half2 up = __hsub2_rn(*reinterpret_cast<__half2 *>(&u), kmagic);
+            lo = __hsub2_rn(__hmul2_rn(D2, lo), M2);
+            up = __hsub2_rn(__hmul2_rn(D2, up), M2);
             out[2 * i] = pack_h2_to_act<ACT>(lo);
             out[2 * i + 1] = pack_h2_to_act<ACT>(up);
         }

@@ -116,7 +116,7 @@ template <int ACT> __device__ __forceinline__ void mma_16x8x16(float (&d)[4], ui
 }
 
 template <class Q, int MATH, int ACT>
-__global__ void __launch_bounds__(kGemvThreads, 4) gemv_mma_kernel(const uint8_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
+__global__ void __launch_bounds__(kGemvThreads) gemv_mma_kernel(const uint8_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
                                                                 long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
                                                                 uint8_t *__restrict__ Y, long long ldy)
 {

@@ -179,6 +179,27 @@ def test_non_lora_patch_takes_two_step_route(pkg):
     assert lin._lora_terms(torch.device(DEV)) is None
 
 
+@pytest.mark.parametrize("M", [3, 300])
+def test_q4k_producer_is_exact_for_huge_scales(pkg, M):
+    """The hand-scheduled Q4_K producer folds `fp16(D*q)` into one fma, which needs 2^k*D to be representable; sub-blocks
+    with |d*sc| >= 32 must fall back to the plain sequence instead of overflowing to NaN.  d = 4.0 gives D = 4*sc in
+    [0, 252]: lanes of both kinds inside the same warp."""
+    N, K = 264, 1024
+    raw = oracle.random_blocks(int(Q.Q4_K), N * K // 256, seed=11, scale=0.02).reshape(-1, 144).copy()
+    raw[:, 0:2] = np.frombuffer(np.float16(4.0).tobytes(), dtype=np.uint8)
+    raw = raw.reshape(N, K // 256 * 144)
+    w = pkg.ops.GGMLTensor(torch.from_numpy(raw).to(DEV), tensor_type=Q.Q4_K, tensor_shape=torch.Size((N, K)))
+    W = pkg.ops._plain(pkg.dequant.dequantize_tensor(w, torch.bfloat16))       # K1: bit-exact vs the reference
+    assert torch.isfinite(W).all() and W.abs().max() > 1000
+    x = (torch.randn(M, K, device=DEV) * 0.01).to(torch.bfloat16)
+    ref = torch.nn.functional.linear(x.double(), W.double())
+    algos = [pkg.lib.ALGO_AUTO] if M <= 8 else [pkg.lib.ALGO_FUSED_MMA, pkg.lib.ALGO_DEQUANT_MMA]
+    for algo in algos:
+        y = pkg.ops.linear_packed(x, w, None, None, algo)
+        assert torch.isfinite(y).all()
+        assert float((y.double() - ref).norm() / ref.norm()) <= 3e-3   # bf16 output rounding of values ~1e2
+
+
 def test_embedding_row_gather_equals_reference_semantics(pkg):
     emb = pkg.ops.GGMLOps.Embedding(500, 1024, device="meta")
     raw, w = _weight(pkg, Q.Q5_K, 500, 1024, seed=8)
