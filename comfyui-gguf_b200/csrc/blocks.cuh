@@ -27,10 +27,10 @@ enum : int {
 };
 
 // spread the low four bits of t over the low bit of four bytes (bit i -> byte i)
-__device__ __forceinline__ uint32_t spread4(uint32_t t) { return ((t & 0xFu) * 0x00204081u) & 0x01010101u; }
+GG_HD uint32_t spread4(uint32_t t) { return ((t & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 // dequant.py:241 value table, stored biased by +127 so it fits unsigned bytes
-__device__ __forceinline__ uint32_t iq4_lookup4(uint32_t idx4)
+GG_HD uint32_t iq4_lookup4(uint32_t idx4)
 {
     // entries 0..15 of (KVALUES + 127):  0 23 44 62 | 78 92 105 117 | 128 140 152 165 | 180 196 216 240
     const uint32_t t0 = 0x3E2C1700u, t1 = 0x75695C4Eu, t2 = 0xA5988C80u, t3 = 0xF0D8C4B4u;
@@ -49,70 +49,70 @@ template <int QT> struct Block;
 // ---------------------------------------------------------------- legacy 32-element blocks
 template <> struct Block<T_Q4_0> {  // dequant.py:115-123   [d f16][qs 16]
     static constexpr int BS = 32, TS = 18, BIAS = 8, KIND = 0, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         return (ld32<2>(b + 2 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
     }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 template <> struct Block<T_Q4_1> {  // dequant.py:103-113   [d][m][qs 16]
     static constexpr int BS = 32, TS = 20, BIAS = 0, KIND = 1, A_BLK = 4;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<4>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<4>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         return (ld32<4>(b + 4 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
     }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 template <> struct Block<T_Q5_0> {  // dequant.py:87-101   [d][qh u32][qs 16]
     static constexpr int BS = 32, TS = 22, BIAS = 16, KIND = 0, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         uint32_t qh = ld32<2>(b + 2);
         uint32_t lo = (ld32<2>(b + 6 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
         return lo | (spread4(qh >> e0) << 4);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 template <> struct Block<T_Q5_1> {  // dequant.py:71-85   [d][m][qh u32][qs 16]
     static constexpr int BS = 32, TS = 24, BIAS = 0, KIND = 1, A_BLK = 8;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         uint32_t qh = ld32<4>(b + 4);
         uint32_t lo = (ld32<4>(b + 8 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu;
         return lo | (spread4(qh >> e0) << 4);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 template <> struct Block<T_Q8_0> {  // dequant.py:65-69   [d][int8 x 32]
     static constexpr int BS = 32, TS = 34, BIAS = 128, KIND = 0, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0) { return ld32<2>(b + 2 + e0) ^ 0x80808080u; }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0) { return ld32<2>(b + 2 + e0) ^ 0x80808080u; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 template <> struct Block<T_IQ4_NL> {  // dequant.py:243-256   layout of Q4_0, values through the table
     static constexpr int BS = 32, TS = 18, BIAS = 127, KIND = 0, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         return iq4_lookup4((ld32<2>(b + 2 + (e0 & 15)) >> (4 * (e0 >> 4))) & 0x0F0F0F0Fu);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
+    static GG_HD void scales(const uint8_t *, int, int &sc, int &mn) { sc = 1; mn = 0; }
 };
 
 // ---------------------------------------------------------------- K-quants, 256-element super-blocks
 // dequant.py:129-139: eight 6-bit (scale, min) pairs in 12 bytes s[0..11]
 // branch-free: the three little-endian words w0 = s[0..3], w1 = s[4..7], w2 = s[8..11]
-__device__ __forceinline__ void k_scale_min(const uint8_t *s, int j, int &sc, int &mn)
+GG_HD void k_scale_min(const uint8_t *s, int j, int &sc, int &mn)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(s);   // blk + 4 is 4-byte aligned for Q4_K / Q5_K
     const int sh = 8 * (j & 3);
@@ -124,13 +124,13 @@ __device__ __forceinline__ void k_scale_min(const uint8_t *s, int j, int &sc, in
 
 template <> struct Block<T_Q2_K> {  // dequant.py:221-238   [scales 16][qs 64][d][dmin]
     static constexpr int BS = 256, TS = 84, BIAS = 0, KIND = 3, A_BLK = 4;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<4>(b + 80); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 82); }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<4>(b + 80); }
+    static GG_HD uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 82); }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         return (ld32<4>(b + 16 + 32 * (e0 >> 7) + (e0 & 31)) >> (2 * ((e0 >> 5) & 3))) & 0x03030303u;
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         uint32_t s = b[e0 >> 4];
         sc = s & 0x0F;
@@ -139,15 +139,15 @@ template <> struct Block<T_Q2_K> {  // dequant.py:221-238   [scales 16][qs 64][d
 };
 template <> struct Block<T_Q3_K> {  // dequant.py:197-219   [hmask 32][qs 64][scales 12][d]
     static constexpr int BS = 256, TS = 110, BIAS = 4, KIND = 2, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 108); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 108); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         uint32_t lo = (ld32<2>(b + 32 + 32 * (e0 >> 7) + (e0 & 31)) >> (2 * ((e0 >> 5) & 3))) & 0x03030303u;
         uint32_t hb = (ld32<2>(b + (e0 & 31)) >> (e0 >> 5)) & 0x01010101u;
         return lo + (hb << 2);  // q = lo - 4*(hb^1) = lo + 4*hb - 4
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         int i = e0 >> 4;
         uint32_t ls = (b[96 + (i & 7)] >> (4 * (i >> 3))) & 0x0F;
@@ -158,45 +158,45 @@ template <> struct Block<T_Q3_K> {  // dequant.py:197-219   [hmask 32][qs 64][sc
 };
 template <> struct Block<T_Q4_K> {  // dequant.py:180-195   [d][dmin][scales 12][qs 128]
     static constexpr int BS = 256, TS = 144, BIAS = 0, KIND = 3, A_BLK = 16;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         return (ld32<4>(b + 16 + 32 * (e0 >> 6) + (e0 & 31)) >> (4 * ((e0 >> 5) & 1))) & 0x0F0F0F0Fu;
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         k_scale_min(b + 4, e0 >> 5, sc, mn);
     }
 };
 template <> struct Block<T_Q5_K> {  // dequant.py:159-178   [d][dmin][scales 12][qh 32][qs 128]
     static constexpr int BS = 256, TS = 176, BIAS = 0, KIND = 3, A_BLK = 16;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<16>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *b) { return ld16<2>(b + 2); }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         int sb = e0 >> 5;
         uint32_t lo = (ld32<4>(b + 48 + 32 * (e0 >> 6) + (e0 & 31)) >> (4 * (sb & 1))) & 0x0F0F0F0Fu;
         uint32_t hi = (ld32<4>(b + 16 + (e0 & 31)) >> sb) & 0x01010101u;
         return lo | (hi << 4);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         k_scale_min(b + 4, e0 >> 5, sc, mn);
     }
 };
 template <> struct Block<T_Q6_K> {  // dequant.py:141-157   [ql 128][qh 64][scales i8 16][d]
     static constexpr int BS = 256, TS = 210, BIAS = 32, KIND = 2, A_BLK = 2;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 208); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<2>(b + 208); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         int h = e0 >> 7, r = e0 & 127;
         uint32_t lo = (ld32<2>(b + 64 * h + (r & 63)) >> (4 * (r >> 6))) & 0x0F0F0F0Fu;
         uint32_t hi = (ld32<2>(b + 128 + 32 * h + (r & 31)) >> (2 * (r >> 5))) & 0x03030303u;
         return lo | (hi << 4);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         sc = (int)(int8_t)b[192 + (e0 >> 4)];
         mn = 0;
@@ -204,15 +204,15 @@ template <> struct Block<T_Q6_K> {  // dequant.py:141-157   [ql 128][qh 64][scal
 };
 template <> struct Block<T_IQ4_XS> {  // dequant.py:258-285   [d][scales_h u16][scales_l 4][qs 128]
     static constexpr int BS = 256, TS = 136, BIAS = 127, KIND = 2, A_BLK = 8;
-    static __device__ __forceinline__ uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
-    static __device__ __forceinline__ uint32_t d2_bits(const uint8_t *) { return 0; }
-    static __device__ __forceinline__ uint32_t q4(const uint8_t *b, int e0)
+    static GG_HD uint32_t d_bits(const uint8_t *b) { return ld16<8>(b); }
+    static GG_HD uint32_t d2_bits(const uint8_t *) { return 0; }
+    static GG_HD uint32_t q4(const uint8_t *b, int e0)
     {
         int i = e0 >> 5;
         uint32_t idx = (ld32<4>(b + 8 + 16 * i + (e0 & 15)) >> (4 * ((e0 >> 4) & 1))) & 0x0F0F0F0Fu;
         return iq4_lookup4(idx);
     }
-    static __device__ __forceinline__ void scales(const uint8_t *b, int e0, int &sc, int &mn)
+    static GG_HD void scales(const uint8_t *b, int e0, int &sc, int &mn)
     {
         int i = e0 >> 5;
         uint32_t sh = ld16<2>(b + 2);
@@ -236,7 +236,7 @@ template <int MATH> struct GroupScale {
     typename Math<MATH>::T2 a, b;
 };
 
-template <class Q, int MATH> __device__ __forceinline__ GroupScale<MATH> group_scale(const uint8_t *blk, int e0)
+template <class Q, int MATH> GG_HD GroupScale<MATH> group_scale(const uint8_t *blk, int e0)
 {
     using M = Math<MATH>;
     GroupScale<MATH> g;
@@ -260,7 +260,7 @@ template <class Q, int MATH> __device__ __forceinline__ GroupScale<MATH> group_s
 // N consecutive elements (N = 4 or 8, e0 % N == 0, all inside one group) -> N/2 pairs in the math dtype,
 // op order and per-op rounding exactly as the reference (see oracle/gguf_oracle.c::float_step).
 template <class Q, int MATH, int N>
-__device__ __forceinline__ void dequant_elems(const uint8_t *blk, int e0, const GroupScale<MATH> &g, typename Math<MATH>::T2 (&out)[N / 2])
+GG_HD void dequant_elems(const uint8_t *blk, int e0, const GroupScale<MATH> &g, typename Math<MATH>::T2 (&out)[N / 2])
 {
     using M = Math<MATH>;
     static_assert(N == 4 || N == 8, "run length");
@@ -290,7 +290,7 @@ template <class Q, int ACT> struct Fast16 {
     static constexpr bool available = false;
 };
 
-template <int ACT> __device__ __forceinline__ uint32_t pack_h2_to_act(__half2 v)
+template <int ACT> GG_HD uint32_t pack_h2_to_act(__half2 v)
 {
     if constexpr (ACT == kF16) {
         return *reinterpret_cast<uint32_t *>(&v);
@@ -303,7 +303,7 @@ template <int ACT> __device__ __forceinline__ uint32_t pack_h2_to_act(__half2 v)
 
 template <int ACT> struct Fast16<Block<T_Q4_K>, ACT> {
     static constexpr bool available = true;
-    static __device__ __forceinline__ void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
+    static GG_HD void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
     {
         const uint4 h = *reinterpret_cast<const uint4 *>(blk);                 // d | dmin<<16, scales[0..11]
         const int sb = e0 >> 5;                                               // sub-block 0..7
@@ -345,7 +345,7 @@ template <int ACT> struct Fast16<Block<T_Q4_K>, ACT> {
 template <int ACT> struct Fast16<Block<T_Q8_0>, ACT> {
     static constexpr bool available = true;
     // a 34-byte block is only 2-byte aligned: assemble the sixteen int8 from 16-bit loads
-    static __device__ __forceinline__ void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
+    static GG_HD void run(const uint8_t *blk, int e0, uint32_t (&out)[8])
     {
         const uint16_t *p16 = reinterpret_cast<const uint16_t *>(blk);
         const __half2 D2 = __half2half2(__ushort_as_half(p16[0]));
@@ -364,7 +364,7 @@ template <int ACT> struct Fast16<Block<T_Q8_0>, ACT> {
 };
 
 template <class Q, int MATH, int N>
-__device__ __forceinline__ void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
+GG_HD void dequant_run(const uint8_t *blk, int e0, typename Math<MATH>::T2 (&out)[N / 2])
 {
     const GroupScale<MATH> g = group_scale<Q, MATH>(blk, e0);
     dequant_elems<Q, MATH, N>(blk, e0, g, out);

@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/ggufb200.h"
 
@@ -18,6 +19,11 @@ namespace ggufb200 {
 constexpr int kF16 = GGUFB200_F16;
 constexpr int kBF16 = GGUFB200_BF16;
 constexpr int kF32 = GGUFB200_F32;
+
+// The per-format unpack functors (blocks.cuh) and the math policies below are pure functions of their arguments, so they
+// are compiled for the host as well: tests/host_functors.cu runs them on the CPU and compares them bit for bit with the
+// oracle, which checks the DEVICE arithmetic without a GPU.  Device code generation is unaffected (same SASS).
+#define GG_HD __host__ __device__ __forceinline__
 
 // ------------------------------------------------------------------ PTX: smem / mbarrier / bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,16 +85,68 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+GG_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
+#ifdef __CUDA_ARCH__
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
+#else
+    // PTX prmt.b32, default mode: selector nibble i picks byte (n & 7) of {b, a}; bit 3 replicates that byte's sign
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t n = (sel >> (4 * i)) & 0xFu;
+        uint32_t byte = (uint32_t)(pool >> (8 * (n & 7u))) & 0xFFu;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xFFu : 0x00u;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+
+// round-to-nearest binary32 ops that the compiler may not contract into an fma (device: the _rn intrinsics)
+GG_HD float f32_mul(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+GG_HD float f32_add(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+GG_HD float f32_sub(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b;
+    return r;
+#endif
+}
+GG_HD float f32_from_bits(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
 }
 
 // ------------------------------------------------------------------ aligned-as-known loads from a byte pointer
 // A = compile-time known alignment of p (1, 2, 4, 8, 16); works for shared and global.
-template <int A> __device__ __forceinline__ uint32_t ld32(const uint8_t *p)
+template <int A> GG_HD uint32_t ld32(const uint8_t *p)
 {
     if constexpr (A >= 4) {
         return *reinterpret_cast<const uint32_t *>(p);
@@ -99,7 +157,7 @@ template <int A> __device__ __forceinline__ uint32_t ld32(const uint8_t *p)
         return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
     }
 }
-template <int A> __device__ __forceinline__ uint32_t ld16(const uint8_t *p)
+template <int A> GG_HD uint32_t ld16(const uint8_t *p)
 {
     if constexpr (A >= 2) {
         return *reinterpret_cast<const uint16_t *>(p);
@@ -118,14 +176,14 @@ template <int MATH> struct Math;
 template <> struct Math<kF16> {
     using T = __half;
     using T2 = __half2;
-    static __device__ __forceinline__ T from_h(uint32_t bits) { return __ushort_as_half((unsigned short)bits); }
-    static __device__ __forceinline__ T from_int(int i) { return __int2half_rn(i); }
-    static __device__ __forceinline__ T mul(T a, T b) { return __hmul_rn(a, b); }
-    static __device__ __forceinline__ T2 bcast(T a) { return __half2half2(a); }
-    static __device__ __forceinline__ T2 mul2(T2 a, T2 b) { return __hmul2_rn(a, b); }
-    static __device__ __forceinline__ T2 add2(T2 a, T2 b) { return __hadd2_rn(a, b); }
-    static __device__ __forceinline__ T2 sub2(T2 a, T2 b) { return __hsub2_rn(a, b); }
-    static __device__ __forceinline__ void cvt4(uint32_t v, int bias, T2 &lo, T2 &hi)
+    static GG_HD T from_h(uint32_t bits) { return __ushort_as_half((unsigned short)bits); }
+    static GG_HD T from_int(int i) { return __int2half_rn(i); }
+    static GG_HD T mul(T a, T b) { return __hmul_rn(a, b); }
+    static GG_HD T2 bcast(T a) { return __half2half2(a); }
+    static GG_HD T2 mul2(T2 a, T2 b) { return __hmul2_rn(a, b); }
+    static GG_HD T2 add2(T2 a, T2 b) { return __hadd2_rn(a, b); }
+    static GG_HD T2 sub2(T2 a, T2 b) { return __hsub2_rn(a, b); }
+    static GG_HD void cvt4(uint32_t v, int bias, T2 &lo, T2 &hi)
     {
         // bytes -> fp16 (1024 + u) by OR-ing the exponent pattern 0x64, then subtract (1024 + bias): exact
         uint32_t l = prmt(v, 0x64646464u, 0x4140u);
@@ -134,34 +192,34 @@ template <> struct Math<kF16> {
         lo = __hsub2_rn(*reinterpret_cast<__half2 *>(&l), off);
         hi = __hsub2_rn(*reinterpret_cast<__half2 *>(&h), off);
     }
-    static __device__ __forceinline__ float2 to_f32x2(T2 a) { return __half22float2(a); }
+    static GG_HD float2 to_f32x2(T2 a) { return __half22float2(a); }
 };
 
 template <int MATH> struct MathF {  // binary32 carrier, rounded to MATH after every op
     using T = float;
     using T2 = float2;
-    static __device__ __forceinline__ float r(float x)
+    static GG_HD float r(float x)
     {
         if constexpr (MATH == kBF16) return __bfloat162float(__float2bfloat16_rn(x));
         else return x;
     }
-    static __device__ __forceinline__ T from_h(uint32_t bits) { return r(__half2float(__ushort_as_half((unsigned short)bits))); }
-    static __device__ __forceinline__ T from_int(int i) { return (float)i; }
-    static __device__ __forceinline__ T mul(T a, T b) { return r(__fmul_rn(a, b)); }
-    static __device__ __forceinline__ T2 bcast(T a) { return make_float2(a, a); }
-    static __device__ __forceinline__ T2 mul2(T2 a, T2 b) { return make_float2(r(__fmul_rn(a.x, b.x)), r(__fmul_rn(a.y, b.y))); }
-    static __device__ __forceinline__ T2 add2(T2 a, T2 b) { return make_float2(r(__fadd_rn(a.x, b.x)), r(__fadd_rn(a.y, b.y))); }
-    static __device__ __forceinline__ T2 sub2(T2 a, T2 b) { return make_float2(r(__fsub_rn(a.x, b.x)), r(__fsub_rn(a.y, b.y))); }
-    static __device__ __forceinline__ void cvt4(uint32_t v, int bias, T2 &lo, T2 &hi)
+    static GG_HD T from_h(uint32_t bits) { return r(__half2float(__ushort_as_half((unsigned short)bits))); }
+    static GG_HD T from_int(int i) { return (float)i; }
+    static GG_HD T mul(T a, T b) { return r(f32_mul(a, b)); }
+    static GG_HD T2 bcast(T a) { return make_float2(a, a); }
+    static GG_HD T2 mul2(T2 a, T2 b) { return make_float2(r(f32_mul(a.x, b.x)), r(f32_mul(a.y, b.y))); }
+    static GG_HD T2 add2(T2 a, T2 b) { return make_float2(r(f32_add(a.x, b.x)), r(f32_add(a.y, b.y))); }
+    static GG_HD T2 sub2(T2 a, T2 b) { return make_float2(r(f32_sub(a.x, b.x)), r(f32_sub(a.y, b.y))); }
+    static GG_HD void cvt4(uint32_t v, int bias, T2 &lo, T2 &hi)
     {
         // bytes -> fp32 (2^23 + u) via exponent pattern 0x4B000000, then subtract (2^23 + bias): exact
         const float off = 8388608.0f + (float)bias;
-        lo.x = __fsub_rn(__uint_as_float(prmt(v, 0x4B000000u, 0x7650u)), off);
-        lo.y = __fsub_rn(__uint_as_float(prmt(v, 0x4B000000u, 0x7651u)), off);
-        hi.x = __fsub_rn(__uint_as_float(prmt(v, 0x4B000000u, 0x7652u)), off);
-        hi.y = __fsub_rn(__uint_as_float(prmt(v, 0x4B000000u, 0x7653u)), off);
+        lo.x = f32_sub(f32_from_bits(prmt(v, 0x4B000000u, 0x7650u)), off);
+        lo.y = f32_sub(f32_from_bits(prmt(v, 0x4B000000u, 0x7651u)), off);
+        hi.x = f32_sub(f32_from_bits(prmt(v, 0x4B000000u, 0x7652u)), off);
+        hi.y = f32_sub(f32_from_bits(prmt(v, 0x4B000000u, 0x7653u)), off);
     }
-    static __device__ __forceinline__ float2 to_f32x2(T2 a) { return a; }
+    static GG_HD float2 to_f32x2(T2 a) { return a; }
 };
 template <> struct Math<kBF16> : MathF<kBF16> {};
 template <> struct Math<kF32> : MathF<kF32> {};
@@ -181,7 +239,7 @@ template <> struct OutT<kF32> {
     static constexpr int bytes = 4;
 };
 
-template <int OUT, int MATH> __device__ __forceinline__ uint32_t pack16(typename Math<MATH>::T2 v)
+template <int OUT, int MATH> GG_HD uint32_t pack16(typename Math<MATH>::T2 v)
 {
     static_assert(OUT != kF32, "pack16 is for 16-bit outputs");
     if constexpr (OUT == kF16 && MATH == kF16) {
