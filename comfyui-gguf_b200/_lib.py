@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
     L.ggufb200_dequant.argtypes = [c_int, c_vp, c_i64, c_vp, c_int, c_int, c_vp]
     L.ggufb200_unpack_int.argtypes = [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.ggufb200_dequant_rows.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]
+    L.ggufb200_linear_plan.restype = c_int
+    L.ggufb200_linear_plan.argtypes = [c_int, c_i64, c_i64, c_i64, c_sz] + [ctypes.POINTER(c_int)] * 4
     L.ggufb200_linear_workspace.restype = c_sz
     L.ggufb200_linear_workspace.argtypes = [c_int, c_i64, c_i64, c_i64, c_int, c_int]
     L.ggufb200_linear.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_vp, c_i64,
@@ -69,5 +71,5 @@ def check(rc: int, what: str) -> None:
 EXPORTS = (
     "ggufb200_version", "ggufb200_strerror", "ggufb200_type_info", "ggufb200_supported", "ggufb200_dequant",
     "ggufb200_unpack_int", "ggufb200_dequant_rows", "ggufb200_linear_workspace", "ggufb200_linear", "ggufb200_gemm",
-    "ggufb200_set_tuning",
+    "ggufb200_set_tuning", "ggufb200_linear_plan",
 )

@@ -21,6 +21,7 @@ int gemm_dense_dispatch(const void *W, long long N, long long K, long long ldw, 
 int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
                          int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st);
 int gemm2_fused_splits(long long M, long long N, long long K);
+void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int *accs, int *splits, int *kb_per_split, int *ctas);
 int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                          int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
@@ -254,6 +255,19 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     }
     }
     return GGUFB200_E_UNSUPPORTED;
+}
+
+int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int *tile_rows, int *k_ranges,
+                         int *kblocks_per_range, int *ctas)
+{
+    if (!type_geom(ggml_type, nullptr, nullptr)) return GGUFB200_E_TYPE;
+    if (!tile_rows || !k_ranges || !kblocks_per_range || !ctas) return GGUFB200_E_NULL;
+    if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 8 != 0) return GGUFB200_E_SHAPE;
+    if (!gemm_fused_supported(ggml_type) || g_gemm_variant < 1) return GGUFB200_E_UNSUPPORTED;
+    int accs = 1;
+    gemm2_fused_plan_info(M, N, K, workspace_bytes, &accs, k_ranges, kblocks_per_range, ctas);
+    *tile_rows = 256 * accs;
+    return GGUFB200_OK;
 }
 
 int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx, int act_dtype,

@@ -439,6 +439,25 @@ static G2Plan g2_fused_plan(long long M, long long N, long long K, size_t ws_byt
 // split-K factor the fused route would use given a workspace (ggufb200_linear_workspace / AUTO routing)
 int gemm2_fused_splits(long long M, long long N, long long K) { return g2_fused_plan(M, N, K, kG2SplitWsCap).splits; }
 
+// k-blocks (64 wide) each K range walks: whole 256-wide spans, the last range may be shorter but never empty
+static int g2_kb_per_split(long long K, int splits)
+{
+    if (splits <= 1) return (int)(K / kG2BK);
+    const int spans = (int)(K / kG2Span);
+    return ((spans + splits - 1) / splits) * 4;
+}
+
+// diagnostics (ggufb200_linear_plan): the tiling the fused kernel uses for this problem and workspace size
+void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int *accs, int *splits, int *kb_per_split, int *ctas)
+{
+    const G2Plan plan = g2_fused_plan(M, N, K, ws_bytes);
+    const long long tiles = ((M + 256 * plan.accs - 1) / (256 * plan.accs)) * ((N + kG2BN - 1) / kG2BN);
+    *accs = plan.accs;
+    *splits = plan.splits;
+    *kb_per_split = g2_kb_per_split(K, plan.splits);
+    *ctas = (int)(2 * tiles * plan.splits);
+}
+
 template <class Q, int MATH, int ACT, int ACCS, bool STAGED = false>
 static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2Params &p, cudaStream_t st)
 {
@@ -451,13 +470,7 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
     const long long tiles_n = (p.N + kG2BN - 1) / kG2BN;
     q.n_tiles = (int)(q.tiles_m * tiles_n);
     const int splits = p.partial ? p.splits : 1;
-    const int total_kb = (int)(p.K / kG2BK);
-    if (splits > 1) {
-        const int spans = (int)(p.K / kG2Span);
-        q.kb_per_split = ((spans + splits - 1) / splits) * 4;
-    } else {
-        q.kb_per_split = total_kb;
-    }
+    q.kb_per_split = g2_kb_per_split(p.K, splits);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * q.n_tiles * splits));
     cfg.blockDim = dim3(STAGED ? 768 : kG2Threads);

@@ -134,6 +134,12 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
 int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx,
                   int act_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream);
 
+/* Diagnostics: the tiling GGUFB200_ALGO_FUSED_MMA uses for this problem when given `workspace_bytes` of scratch --
+ * activation rows per SM-pair tile (256 or 512), number of K ranges (1 = unsplit), 64-wide k-blocks per range (the last
+ * range may be shorter, never empty) and the number of CTAs launched.  Pure host arithmetic, no GPU needed. */
+int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int *tile_rows, int *k_ranges,
+                         int *kblocks_per_range, int *ctas);
+
 /* Tuning knobs for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default),
  * key 1 = programmatic dependent launch of the dequant kernel (default 1),
  * key 2 = tensor-core GEMM variant: 2 = CTA-pair UMMA + persistent double-buffered dense GEMM (default),

@@ -1,0 +1,81 @@
+"""Host arithmetic of the fused Linear's tiling (csrc/gemm2.cu::g2_fused_plan, exported as ggufb200_linear_plan).
+
+A wrong plan is the kind of bug that HANGS a GPU (a K range with no k-blocks never signals its barriers), so the invariants
+are checked here on the CPU over many shapes: every K range owns whole 256-wide spans, none is empty, together they cover K
+exactly once, the slices fit the workspace, the grid fits the 74 SM pairs when K is split, and the workspace query, the plan
+and the AUTO routing agree with each other."""
+import ctypes
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from util import Q
+
+PAIRS = 74          # 148 SMs (sm_count() reports 148 without a device as well)
+CAP = 64 << 20
+
+
+def _plan(L, qt, M, N, K, ws):
+    vals = [ctypes.c_int() for _ in range(4)]
+    rc = L.ggufb200_linear_plan(int(qt), M, N, K, ws, *[ctypes.byref(v) for v in vals])
+    return rc, tuple(v.value for v in vals)
+
+
+def _check(L, M, N, K, ws):
+    rc, (rows, ranges, kb, ctas) = _plan(L, Q.Q4_K, M, N, K, ws)
+    assert rc == 0
+    assert rows in (256, 512) and ranges >= 1 and kb >= 1
+    total_kb = K // 64
+    tiles = -(-M // rows) * -(-N // 256)
+    assert ctas == 2 * tiles * ranges
+    if ranges == 1:
+        assert kb == total_kb
+        return ranges
+    assert K % 256 == 0 and kb % 4 == 0                        # whole spans per range
+    assert (ranges - 1) * kb < total_kb <= ranges * kb          # no empty range, full cover
+    assert ranges <= 16 and tiles * ranges <= PAIRS             # one wave of SM pairs
+    assert ranges * M * N * 4 <= min(ws, CAP)                   # slices fit what the caller gave (and the L2 budget)
+    if M > 256:
+        assert rows == 512 or -(-M // 512) * -(-N // 256) * 2 > PAIRS
+    return ranges
+
+
+def test_known_plans(pkg):
+    L = pkg.lib.lib()
+    L.ggufb200_set_tuning(2, 2), L.ggufb200_set_tuning(6, 1)
+    assert _plan(L, Q.Q4_K, 512, 3072, 12288, CAP) == (0, (512, 6, 32, 144))      # the ncu'd launch: 12 tiles x 6 ranges
+    assert _plan(L, Q.Q5_K, 512, 4096, 4096, CAP) == (0, (512, 4, 16, 128))        # T5 q/k/v/o
+    assert _plan(L, Q.Q4_K, 4608, 3072, 3072, CAP)[1][1] == 1                      # plenty of tiles: unsplit
+    assert _plan(L, Q.Q4_K, 512, 3072, 12288, 0)[1][1] == 1                        # no workspace: unsplit
+    assert _plan(L, Q.Q4_K, 512, 3072, 12288, 3 * 512 * 3072 * 4)[1][1] == 3       # smaller workspace: fewer ranges
+    assert _plan(L, Q.Q4_K, 64, 512, 4096 + 64, CAP)[1][1] == 1                    # K not a multiple of 256: unsplit
+    assert _plan(L, Q.BF16, 64, 512, 4096, CAP)[0] == -8                           # no fused kernel for dense weights
+    assert _plan(L, Q.Q4_K, 64, 512, 4000, CAP)[0] == -4
+    assert _plan(L, 99, 64, 512, 4096, CAP)[0] == -1
+
+
+@settings(max_examples=600, deadline=None)
+@given(M=st.integers(9, 1500), n8=st.integers(1, 3000), k64=st.integers(1, 400), ws_slices=st.integers(0, 20))
+def test_plan_invariants(pkg, M, n8, k64, ws_slices):
+    L = pkg.lib.lib()
+    N, K = 8 * n8, 64 * k64
+    ws = ws_slices * M * N * 4
+    ranges = _check(L, M, N, K, ws)
+    # the size the library asks for is exactly what the plan with that size uses
+    need = L.ggufb200_linear_workspace(int(Q.Q4_K), M, N, K, 1, pkg.lib.ALGO_FUSED_MMA)
+    assert need % (M * N * 4) == 0 and need <= CAP
+    if need:
+        assert _check(L, M, N, K, need) == need // (M * N * 4) >= 2
+    else:
+        assert _check(L, M, N, K, CAP) == 1
+    assert ranges <= max(1, need // (M * N * 4))
+
+
+def test_split_knob_disables_every_split(pkg):
+    L = pkg.lib.lib()
+    L.ggufb200_set_tuning(6, 0)
+    try:
+        for M, N, K in ((64, 512, 4096), (512, 3072, 12288), (1000, 256, 5120)):
+            assert _plan(L, Q.Q4_K, M, N, K, CAP)[1][1] == 1
+    finally:
+        L.ggufb200_set_tuning(6, 1)
