@@ -157,3 +157,25 @@ def test_k_scale_min_and_value_table(hostf):
     # the host stand-in of prmt.b32 follows the PTX definition (byte select + sign replicate)
     assert hostf.hostf_prmt(0x33221100, 0x77665544, 0x7531) == 0x77553311
     assert hostf.hostf_prmt(0x80221100, 0x77665544, 0x000B) == 0x000000FF
+
+
+def test_functors_never_read_past_the_last_block(tmp_path):
+    """AddressSanitizer + UBSan over exact-size heap buffers (1, 3, 16 blocks of every format, every dtype pair, both
+    16-element producers): a functor that over-reads its block would fault on the GPU at the end of an allocation."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    gxx = shutil.which("g++")
+    if not os.path.exists(nvcc) or gxx is None:
+        pytest.skip("toolchain not available")
+    obj, exe = str(tmp_path / "hf.o"), str(tmp_path / "asan_run")
+    san = "-fsanitize=address,-fsanitize=undefined,-fno-sanitize=alignment"   # 2-byte aligned blocks are read with 16-bit loads by design
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-g", "-std=c++17", "--expt-relaxed-constexpr",
+                        "-Xcompiler", "-fPIC,-ffp-contract=off," + san, "-c", SRC, "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not available: " + r.stderr[-200:])
+    cudart = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    r = subprocess.run([gxx, "-fsanitize=address,undefined", "-g", os.path.join(HERE, "host_functors_asan_main.cpp"), obj,
+                        "-L" + cudart, "-lcudart", "-Wl,-rpath," + cudart, "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer link not available: " + r.stderr[-200:])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and "asan run ok" in run.stdout, run.stderr[-2000:]
