@@ -14,7 +14,10 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libggufb200.so")
 _lib = None
 
 F16, BF16, F32 = 0, 1, 2
-ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA = 0, 1, 2, 3
+ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA, ALGO_FUSED_TMEM = 0, 1, 2, 3, 4
+ALGO_MASK = 0xFF
+# per-call switches OR-ed into `algo` (include/ggufb200.h)
+FLAG_EXACT_W, FLAG_GENERIC, FLAG_TILE384, FLAG_NOSPLIT, FLAG_UNSTAGED = 0x100, 0x200, 0x400, 0x800, 0x1000
 OP_DEQUANT, OP_LINEAR, OP_ROWS, OP_LINEAR_MMA = 0, 1, 2, 3
 
 
@@ -53,9 +56,11 @@ def lib() -> ctypes.CDLL:
     L.ggufb200_unpack_int.argtypes = [c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.ggufb200_dequant_rows.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp]
     L.ggufb200_linear_plan.restype = c_int
-    L.ggufb200_linear_plan.argtypes = [c_int, c_i64, c_i64, c_i64, c_sz] + [ctypes.POINTER(c_int)] * 4
+    L.ggufb200_linear_plan.argtypes = [c_int, c_i64, c_i64, c_i64, c_sz, c_int] + [ctypes.POINTER(c_int)] * 4
     L.ggufb200_linear_workspace.restype = c_sz
     L.ggufb200_linear_workspace.argtypes = [c_int, c_i64, c_i64, c_i64, c_int, c_int]
+    L.ggufb200_linear_workspace_ex.restype = c_sz
+    L.ggufb200_linear_workspace_ex.argtypes = [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int]
     L.ggufb200_linear.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_vp, c_i64,
                                   c_vp, c_sz, c_int, c_vp]
     L.ggufb200_gemm.argtypes = [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_vp]
@@ -71,5 +76,5 @@ def check(rc: int, what: str) -> None:
 EXPORTS = (
     "ggufb200_version", "ggufb200_strerror", "ggufb200_type_info", "ggufb200_supported", "ggufb200_dequant",
     "ggufb200_unpack_int", "ggufb200_dequant_rows", "ggufb200_linear_workspace", "ggufb200_linear", "ggufb200_gemm",
-    "ggufb200_set_tuning", "ggufb200_linear_plan",
+    "ggufb200_set_tuning", "ggufb200_linear_plan", "ggufb200_linear_workspace_ex",
 )

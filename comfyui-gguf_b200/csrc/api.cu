@@ -1,70 +1,37 @@
 // api.cu -- the extern "C" boundary declared in include/ggufb200.h.
-// Argument validation lives here; kernels live in dequant.cu / rows.cu / gemv.cu / gemm.cu.
+// Argument validation and route selection live here; kernels live in dequant.cu / rows.cu / gemv.cu / gemm2.cu /
+// gemm3.cu / gemm4.cu / repack.cu.  Routing is a pure function of the call's arguments (algo | flags): no process-wide
+// routing state.
+#include <stdlib.h>
+
 #include "blocks.cuh"
 
 namespace ggufb200 {
 extern int g_dequant_ctas_per_sm;
 extern int g_dequant_pdl;
-extern int g_fused_staged;
-extern int g_gemv_mma;
-extern int g_fused_splitk;
 int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st);
 int unpack_dispatch(int type, const void *packed, long long n_blocks, int16_t *q, int16_t *sc, int16_t *mn, cudaStream_t st);
 int rows_dispatch(int type, const void *packed, long long n_table_rows, long long K, const long long *rows, long long n_rows,
                   void *out, int out_dtype, int math_dtype, cudaStream_t st);
 int gemv_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
                   int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
-int gemm_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
-                        int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
-int gemm_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
-                        int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
-                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st);
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, int flags,
+                         cudaStream_t st);
 int gemm2_fused_splits(long long M, long long N, long long K);
-void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int *accs, int *splits, int *kb_per_split, int *ctas);
-int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
-                         int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *accs, int *splits, int *kb_per_split, int *ctas);
 int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx,
                          int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
-int gemm_fused_supported(int type);
+int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
+                         long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
+                         int flags, cudaStream_t st);
+bool gemm4_supported(int type, const void *W, long long N, long long K);
+size_t gemm4_workspace(long long M, long long N, long long K, int flags);
+void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items);
 int gemv_max_m();
 }  // namespace ggufb200
 
 using namespace ggufb200;
-
-static int g_auto_fused = 0;     // large-M route picked by GGUFB200_ALGO_AUTO: 0 = dequant + tensor-core GEMM, 1 = fused; set_tuning(3, v)
-// 0 = single-CTA UMMA (gemm.cu), 1 = CTA-pair UMMA cta_group::2 (gemm2.cu), 2 = 1 + persistent double-buffered dense GEMM (gemm3.cu)
-static int g_gemm_variant = 2;   // ggufb200_set_tuning(2, v)
-
-static int fused_mma(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act, int math,
-                     const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
-{
-    return g_gemm_variant >= 1 ? gemm2_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, ws, ws_bytes, st)
-                               : gemm_fused_dispatch(type, W, N, K, X, M, ldx, act, math, bias, bias_dtype, Y, ldy, st);
-}
-// GGUFB200_ALGO_AUTO for M > 8, measured on B200 (profiles/): with M >= ~1k the dequant-once + dense GEMM route wins
-// (1.27-1.44 vs 0.87-1.21 PFLOP/s); for short activations the fused kernel wins because the standalone dequant is no longer
-// amortised over many M tiles (and split-K keeps all SM pairs busy while every packed byte is still read once).
-static bool auto_prefers_fused(int type, long long M, long long N, long long K)
-{
-    if (!gemm_fused_supported(type) || (K % 64) != 0) return false;
-    if (g_auto_fused) return true;
-    if (M > 1024) return false;
-    if (g_gemm_variant >= 1) {   // split-K: all SM pairs dequantise in parallel (measured: profiles/r01_bench_linear_graph_m512_m64.log)
-        const int splits = gemm2_fused_splits(M, N, K);
-        if (splits >= 4 || (splits >= 2 && K >= 2 * N)) return true;
-        if (splits >= 2) return false;
-    }
-    return M > 256 && N >= 12288;
-}
-
-static int dense_mma(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act,
-                     const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
-{
-    if (g_gemm_variant == 2) return gemm3_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
-    return g_gemm_variant == 1 ? gemm2_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st)
-                               : gemm_dense_dispatch(W, N, K, ldw, X, M, ldx, act, bias, bias_dtype, Y, ldy, st);
-}
 
 static bool type_geom(int t, int *bs, int *ts)
 {
@@ -92,6 +59,93 @@ static bool type_geom(int t, int *bs, int *ts)
 
 static bool dtype_ok(int d) { return d >= 0 && d <= 2; }
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool fused_type(int t) { return t != T_BF16 && type_geom(t, nullptr, nullptr); }     // every block format has a fused producer
+
+// ------------------------------------------------------------------ device gate
+// The library contains sm_100a code only.  Checked once per device, right before the first launch on it (argument
+// errors are still reported without a GPU).
+static int device_check()
+{
+    static signed char ok[64] = {};     // 0 = unknown, 1 = sm_100, -1 = something else
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return GGUFB200_E_CUDA;
+    }
+    if (dev < 0 || dev >= 64) return GGUFB200_OK;
+    if (ok[dev] == 0) {
+        int major = 0, minor = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return GGUFB200_E_CUDA;
+        }
+        ok[dev] = (major == 10 && minor == 0) ? 1 : -1;
+    }
+    return ok[dev] == 1 ? GGUFB200_OK : GGUFB200_E_DEVICE;
+}
+
+// ------------------------------------------------------------------ route selection
+// Measured on B200 (profiles/):  the TMEM-fed fused kernel serves every M when its contract is acceptable (default);
+// the reference-exact routes keep the round-1 thresholds: M <= 8 mma.sync GEMV, short activations split-K fused through
+// shared memory, long activations dequant once into the workspace + dense tcgen05 GEMM.
+static bool exact_prefers_fused(long long M, long long N, long long K)
+{
+    if ((K % 64) != 0) return false;
+    if (M > 1024) return false;
+    const int splits = gemm2_fused_splits(M, N, K);
+    if (splits >= 4 || (splits >= 2 && K >= 2 * N)) return true;
+    if (splits >= 2) return false;
+    return M > 256 && N >= 12288;
+}
+
+struct Route {
+    int algo;          // GGUFB200_ALGO_* without flags
+    size_t ws;         // workspace bytes the route wants (0 = none)
+};
+
+// ABI flag bits -> gemm4's internal switches (1 = fast producers, 2 = 384-token items, 4 = no split-K)
+static int g4_flags(int flags)
+{
+    int f = (flags & GGUFB200_FLAG_GENERIC) ? 0 : 1;
+    if (flags & GGUFB200_FLAG_TILE384) f |= 2;
+    if (flags & GGUFB200_FLAG_NOSPLIT) f |= 4;
+    return f;
+}
+
+static size_t fused_mma_ws(long long M, long long N, long long K, int flags)
+{
+    if (flags & GGUFB200_FLAG_NOSPLIT) return 0;
+    const int s = gemm2_fused_splits(M, N, K);
+    return s > 1 ? (size_t)s * (size_t)M * (size_t)N * 4 : 0;
+}
+
+// `W` may be NULL (workspace query: assume a 16-byte aligned weight); ws_avail = workspace the caller supplied (SIZE_MAX in a query)
+static Route pick_route(int type, const void *W, long long M, long long N, long long K, int act, int math, int algo_flags, size_t ws_avail)
+{
+    const int algo = algo_flags & GGUFB200_ALGO_MASK;
+    const int flags = algo_flags & ~GGUFB200_ALGO_MASK;
+    const size_t dense = (size_t)N * (size_t)K * 2;
+    const bool w_ok = !W || aligned16(W);
+    const bool fusable = fused_type(type) && math == kF16 && (K % 64) == 0 && (N % 8) == 0;
+    Route r{algo, 0};
+    if (algo == GGUFB200_ALGO_AUTO) {
+        const bool exact = (flags & GGUFB200_FLAG_EXACT_W) != 0 || math != kF16;
+        if (!w_ok) r.algo = GGUFB200_ALGO_DEQUANT_MMA;
+        else if (!exact && fused_type(type) && gemm4_supported(type, W, N, K)) r.algo = GGUFB200_ALGO_FUSED_TMEM;
+        else if (M <= gemv_max_m()) r.algo = GGUFB200_ALGO_GEMV;
+        else if (fusable && (exact_prefers_fused(M, N, K) || ws_avail < dense)) r.algo = GGUFB200_ALGO_FUSED_MMA;
+        else r.algo = GGUFB200_ALGO_DEQUANT_MMA;
+    }
+    switch (r.algo) {
+    case GGUFB200_ALGO_DEQUANT_MMA: r.ws = dense; break;
+    case GGUFB200_ALGO_FUSED_MMA: r.ws = fusable ? fused_mma_ws(M, N, K, flags) : 0; break;
+    case GGUFB200_ALGO_FUSED_TMEM: r.ws = gemm4_workspace(M, N, K, g4_flags(flags)); break;
+    default: r.ws = 0;
+    }
+    (void)act;
+    return r;
+}
 
 extern "C" {
 
@@ -108,7 +162,7 @@ const char *ggufb200_strerror(int rc)
     case GGUFB200_E_NULL: return "required pointer is NULL";
     case GGUFB200_E_CUDA: return "CUDA launch failed";
     case GGUFB200_E_WORKSPACE: return "workspace too small (see ggufb200_linear_workspace)";
-    case GGUFB200_E_UNSUPPORTED: return "operation not implemented for this type / dtype combination";
+    case GGUFB200_E_UNSUPPORTED: return "operation not implemented for this type / dtype / shape combination";
     case GGUFB200_E_DEVICE: return "current CUDA device is not sm_100 (B200)";
     }
     return "unknown error";
@@ -126,39 +180,24 @@ int ggufb200_supported(int ggml_type, int op)
     case GGUFB200_OP_DEQUANT: return 1;
     case GGUFB200_OP_ROWS: return 1;
     case GGUFB200_OP_LINEAR: return 1;
-    case GGUFB200_OP_LINEAR_MMA: return 1;   // fused kernel, or dequant + tensor-core GEMM for types / shapes it does not cover
+    case GGUFB200_OP_LINEAR_MMA: return 1;   // a fused kernel, or dequant + tensor-core GEMM for types / shapes it does not cover
     }
     return 0;
 }
 
 int ggufb200_set_tuning(int key, int value)
 {
+    static const bool allowed = [] {
+        const char *e = getenv("GGUFB200_ALLOW_TUNING");
+        return e && e[0] == '1';
+    }();
+    if (!allowed) return GGUFB200_E_UNSUPPORTED;
     if (key == 0) {
         g_dequant_ctas_per_sm = value;
         return GGUFB200_OK;
     }
     if (key == 1) {
         g_dequant_pdl = value ? 1 : 0;
-        return GGUFB200_OK;
-    }
-    if (key == 2) {
-        g_gemm_variant = value < 0 ? 0 : (value > 2 ? 2 : value);
-        return GGUFB200_OK;
-    }
-    if (key == 3) {
-        g_auto_fused = value ? 1 : 0;
-        return GGUFB200_OK;
-    }
-    if (key == 4) {
-        g_fused_staged = value ? 1 : 0;
-        return GGUFB200_OK;
-    }
-    if (key == 5) {
-        g_gemv_mma = value ? 1 : 0;
-        return GGUFB200_OK;
-    }
-    if (key == 6) {
-        g_fused_splitk = value ? 1 : 0;
         return GGUFB200_OK;
     }
     return GGUFB200_E_UNSUPPORTED;
@@ -172,6 +211,7 @@ int ggufb200_dequant(int ggml_type, const void *packed, int64_t n_blocks, void *
     if (n_blocks == 0) return GGUFB200_OK;
     if (!packed || !out) return GGUFB200_E_NULL;
     if (!aligned16(out)) return GGUFB200_E_ALIGN;
+    if (int rc = device_check()) return rc;
     return dequant_dispatch(ggml_type, packed, n_blocks, out, out_dtype, math_dtype, (cudaStream_t)stream);
 }
 
@@ -181,6 +221,7 @@ int ggufb200_unpack_int(int ggml_type, const void *packed, int64_t n_blocks, int
     if (n_blocks < 0) return GGUFB200_E_SHAPE;
     if (n_blocks == 0) return GGUFB200_OK;
     if (!packed) return GGUFB200_E_NULL;
+    if (int rc = device_check()) return rc;
     return unpack_dispatch(ggml_type, packed, n_blocks, q, sc, mn, (cudaStream_t)stream);
 }
 
@@ -194,20 +235,20 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
     if (n_rows == 0) return GGUFB200_OK;
     if (!packed || !rows || !out) return GGUFB200_E_NULL;
     if (!aligned16(out)) return GGUFB200_E_ALIGN;
+    if (int rc = device_check()) return rc;
     return rows_dispatch(ggml_type, packed, n_table_rows, K, (const long long *)rows, n_rows, out, out_dtype, math_dtype,
                          (cudaStream_t)stream);
 }
 
+size_t ggufb200_linear_workspace_ex(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int math_dtype, int algo)
+{
+    if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0 || M <= 0) return 0;
+    return pick_route(ggml_type, nullptr, M, N, K, act_dtype, math_dtype, algo, (size_t)-1).ws;
+}
+
 size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo)
 {
-    if (!type_geom(ggml_type, nullptr, nullptr) || N <= 0 || K <= 0) return 0;
-    const size_t dense = (size_t)N * (size_t)K * (act_dtype == kF32 ? 4 : 2);
-    const size_t splitk = (g_gemm_variant >= 1 && gemm_fused_supported(ggml_type) && gemm2_fused_splits(M, N, K) > 1)
-                              ? (size_t)gemm2_fused_splits(M, N, K) * (size_t)M * (size_t)N * 4 : 0;
-    if (algo == GGUFB200_ALGO_DEQUANT_MMA) return dense;
-    if (algo == GGUFB200_ALGO_FUSED_MMA) return splitk;          // fp32 partial-result slices of the split-K fused kernel
-    if (algo == GGUFB200_ALGO_AUTO && M > gemv_max_m()) return auto_prefers_fused(ggml_type, M, N, K) ? splitk : dense;
-    return 0;
+    return ggufb200_linear_workspace_ex(ggml_type, M, N, K, act_dtype, kF16, algo);
 }
 
 int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx, int act_dtype,
@@ -221,51 +262,69 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     if (M < 0 || N <= 0 || K <= 0 || K % bs != 0 || K % 8 != 0 || ldx < K || ldy < N) return GGUFB200_E_SHAPE;
     if (M == 0) return GGUFB200_OK;
     if (!W_packed || !X || !Y) return GGUFB200_E_NULL;
-    if (!aligned16(X) || !aligned16(Y) || (ldx % 8) != 0 || (ldy % 8) != 0) return GGUFB200_E_ALIGN;
+    const int flags = algo & ~GGUFB200_ALGO_MASK;
+    const bool w_ok = aligned16(W_packed);
+    const size_t dense = (size_t)N * (size_t)K * 2;
+    const size_t ws_avail = (workspace && aligned16(workspace)) ? workspace_bytes : 0;
+    // The fused producers read the packed rows with the per-format natural alignment (up to 16 bytes).  A packed tensor
+    // that does not start on a 16-byte boundary (never produced by torch allocations, only by byte-offset views) is
+    // always routed through the standalone dequant kernel, which stages any alignment, plus the dense GEMM.
+    if (!w_ok) {
+        if (ws_avail < dense) return GGUFB200_E_ALIGN;
+        algo = GGUFB200_ALGO_DEQUANT_MMA | flags;
+    }
+    const Route r = pick_route(ggml_type, W_packed, M, N, K, act_dtype, math_dtype, algo, ws_avail);
+    // the small-M kernel stores per element: it only needs 2-byte aligned Y rows; every other route moves 16-byte vectors
+    const bool vec_y = r.algo != GGUFB200_ALGO_GEMV;
+    if (!aligned16(X) || (ldx % 8) != 0) return GGUFB200_E_ALIGN;
+    if (vec_y && (!aligned16(Y) || (ldy % 8) != 0)) return GGUFB200_E_ALIGN;
+    if (workspace && !aligned16(workspace) && r.ws) return GGUFB200_E_ALIGN;
+    if (int rc = device_check()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 
-    // The GEMV / fused producers read the packed rows with the per-format natural alignment (up to 16 bytes).  A packed
-    // tensor that does not start on a 16-byte boundary (never produced by torch allocations, only by byte-offset views)
-    // is therefore always routed through the standalone dequant kernel, which stages any alignment, plus the dense GEMM.
-    if (!aligned16(W_packed)) {
-        if (!workspace || workspace_bytes < (size_t)N * (size_t)K * 2) return GGUFB200_E_ALIGN;
-        algo = GGUFB200_ALGO_DEQUANT_MMA;
-    }
-
-    if (algo == GGUFB200_ALGO_AUTO) {
-        const bool ws_ok = workspace && workspace_bytes >= (size_t)N * (size_t)K * 2;
-        const bool fused_ok = gemm_fused_supported(ggml_type) && math_dtype == kF16 && (K % 64) == 0;
-        if (M <= gemv_max_m()) algo = GGUFB200_ALGO_GEMV;
-        else if (fused_ok && (auto_prefers_fused(ggml_type, M, N, K) || !ws_ok)) algo = GGUFB200_ALGO_FUSED_MMA;
-        else algo = GGUFB200_ALGO_DEQUANT_MMA;
-    }
-    switch (algo) {
+    switch (r.algo) {
     case GGUFB200_ALGO_GEMV:
         return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
-    case GGUFB200_ALGO_FUSED_MMA:
-        if (!gemm_fused_supported(ggml_type)) return GGUFB200_E_UNSUPPORTED;
-        return fused_mma(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace, workspace_bytes, st);
+    case GGUFB200_ALGO_FUSED_MMA: {
+        if (!fused_type(ggml_type)) return GGUFB200_E_UNSUPPORTED;
+        int f = 0;
+        if (flags & GGUFB200_FLAG_NOSPLIT) f |= 1;
+        if (flags & GGUFB200_FLAG_UNSTAGED) f |= 2;
+        return gemm2_fused_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace,
+                                    ws_avail, f, st);
+    }
+    case GGUFB200_ALGO_FUSED_TMEM: {
+        if (!fused_type(ggml_type) || math_dtype != kF16) return GGUFB200_E_UNSUPPORTED;
+        return gemm4_fused_dispatch(ggml_type, W_packed, nullptr, 0, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, workspace, ws_avail,
+                                    g4_flags(flags), st);
+    }
     case GGUFB200_ALGO_DEQUANT_MMA: {
-        size_t need = (size_t)N * (size_t)K * 2;
-        if (!workspace || workspace_bytes < need) return GGUFB200_E_WORKSPACE;
-        if (!aligned16(workspace)) return GGUFB200_E_ALIGN;
+        if (ws_avail < dense) return GGUFB200_E_WORKSPACE;
         int rc = dequant_dispatch(ggml_type, W_packed, N * (K / bs), workspace, act_dtype, math_dtype, st);
         if (rc != GGUFB200_OK) return rc;
-        return dense_mma(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
+        return gemm3_dense_dispatch(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
     }
     }
     return GGUFB200_E_UNSUPPORTED;
 }
 
-int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int *tile_rows, int *k_ranges,
+int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int algo, int *tile_rows, int *k_ranges,
                          int *kblocks_per_range, int *ctas)
 {
     if (!type_geom(ggml_type, nullptr, nullptr)) return GGUFB200_E_TYPE;
     if (!tile_rows || !k_ranges || !kblocks_per_range || !ctas) return GGUFB200_E_NULL;
     if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 8 != 0) return GGUFB200_E_SHAPE;
-    if (!gemm_fused_supported(ggml_type) || g_gemm_variant < 1) return GGUFB200_E_UNSUPPORTED;
+    if (!fused_type(ggml_type)) return GGUFB200_E_UNSUPPORTED;
+    const int flags = algo & ~GGUFB200_ALGO_MASK;
+    if ((algo & GGUFB200_ALGO_MASK) == GGUFB200_ALGO_FUSED_TMEM) {
+        int spans = 1;
+        gemm4_plan_info(M, N, K, workspace_bytes, g4_flags(flags), tile_rows, k_ranges, &spans, ctas);
+        *kblocks_per_range = 4 * spans;
+        return GGUFB200_OK;
+    }
+    if ((algo & GGUFB200_ALGO_MASK) != GGUFB200_ALGO_FUSED_MMA) return GGUFB200_E_UNSUPPORTED;
     int accs = 1;
-    gemm2_fused_plan_info(M, N, K, workspace_bytes, &accs, k_ranges, kblocks_per_range, ctas);
+    gemm2_fused_plan_info(M, N, K, workspace_bytes, (flags & GGUFB200_FLAG_NOSPLIT) ? 1 : 0, &accs, k_ranges, kblocks_per_range, ctas);
     *tile_rows = 256 * accs;
     return GGUFB200_OK;
 }
@@ -279,7 +338,8 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
     if (M == 0) return GGUFB200_OK;
     if (!W || !X || !Y) return GGUFB200_E_NULL;
     if (!aligned16(W) || !aligned16(X) || !aligned16(Y) || (ldw % 8) || (ldx % 8) || (ldy % 8)) return GGUFB200_E_ALIGN;
-    return dense_mma(W, N, K, ldw, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, (cudaStream_t)stream);
+    if (int rc = device_check()) return rc;
+    return gemm3_dense_dispatch(W, N, K, ldw, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, (cudaStream_t)stream);
 }
 
 }  // extern "C"

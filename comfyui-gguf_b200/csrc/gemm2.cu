@@ -352,7 +352,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------ host side
-int g_fused_staged = 1;   // ggufb200_set_tuning(4, v): stage packed rows through shared memory in the fused kernel
+// Per-call switches (bits of the `flags` argument; the C ABI passes them inside `algo`, see include/ggufb200.h):
+constexpr int kG2NoSplit = 1;     // never cut the K loop into ranges
+constexpr int kG2Unstaged = 2;    // producers read the packed rows straight from global / L2 (no TMA staging)
 
 // 512-row pair tiles halve the dequant work and the X traffic per flop; fall back to 256-row tiles when the last
 // wave of 512-row tiles would leave too many SM pairs idle
@@ -398,8 +400,6 @@ __global__ void __launch_bounds__(256) g2_finalize_kernel(const float *__restric
 // Split-K factor of the fused kernel: short activations give too few (256*ACCS x 256) tiles for the 74 SM pairs, so the K
 // loop is cut into S ranges of whole 256-wide spans, each handled by its own pair (every packed byte is still read and
 // dequantised exactly once).  Returns 1 when splitting does not apply.
-int g_fused_splitk = 1;   // ggufb200_set_tuning(6, v)
-
 // Tiling of the fused kernel: ACCS (256 or 512 activation rows per pair) and the split-K factor.
 // Short activations give too few (256*ACCS x 256) tiles for the 74 SM pairs, so the K loop is cut into S ranges of whole
 // 256-wide spans, each handled by its own pair, which stores its fp32 partial tile into its own slice of the caller's
@@ -412,12 +412,12 @@ struct G2Plan {
 
 constexpr size_t kG2SplitWsCap = 64u << 20;   // half of the 126 MB L2
 
-static G2Plan g2_fused_plan(long long M, long long N, long long K, size_t ws_bytes)
+static G2Plan g2_fused_plan(long long M, long long N, long long K, size_t ws_bytes, bool allow_split = true)
 {
     G2Plan plan{g2_pick_accs(M, N, true), 1};
     const size_t slice = (size_t)M * (size_t)N * 4;
     if (ws_bytes > kG2SplitWsCap) ws_bytes = kG2SplitWsCap;
-    if (slice == 0 || ws_bytes < 2 * slice || !g_fused_splitk || K % kG2Span != 0) return plan;
+    if (slice == 0 || ws_bytes < 2 * slice || !allow_split || K % kG2Span != 0) return plan;
     const int sms = sm_count();
     const long long pairs = sms / 2;
     const long long tiles_n = (N + kG2BN - 1) / kG2BN;
@@ -448,9 +448,9 @@ static int g2_kb_per_split(long long K, int splits)
 }
 
 // diagnostics (ggufb200_linear_plan): the tiling the fused kernel uses for this problem and workspace size
-void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int *accs, int *splits, int *kb_per_split, int *ctas)
+void gemm2_fused_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *accs, int *splits, int *kb_per_split, int *ctas)
 {
-    const G2Plan plan = g2_fused_plan(M, N, K, ws_bytes);
+    const G2Plan plan = g2_fused_plan(M, N, K, ws_bytes, !(flags & kG2NoSplit));
     const long long tiles = ((M + 256 * plan.accs - 1) / (256 * plan.accs)) * ((N + kG2BN - 1) / kG2BN);
     *accs = plan.accs;
     *splits = plan.splits;
@@ -488,18 +488,18 @@ static int g2_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const Gemm2
 
 template <class Q, int ACT>
 static int g2_fused_once(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
-                         void *Y, long long ldy, float *partial, G2Plan plan, cudaStream_t st);
+                         void *Y, long long ldy, float *partial, G2Plan plan, int flags, cudaStream_t st);
 
 template <class Q, int ACT>
 static int g2_fused_act(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
-                        void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
+                        void *Y, long long ldy, void *ws, size_t ws_bytes, int flags, cudaStream_t st)
 {
     // split-K needs room for the fp32 [splits, M, N] partial results in the caller's workspace
     const bool ws_ok = ws && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
-    const G2Plan plan = g2_fused_plan(M, N, K, ws_ok ? ws_bytes : 0);
-    if (plan.splits <= 1) return g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, nullptr, plan, st);
+    const G2Plan plan = g2_fused_plan(M, N, K, ws_ok ? ws_bytes : 0, !(flags & kG2NoSplit));
+    if (plan.splits <= 1) return g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, nullptr, plan, flags, st);
     float *P = reinterpret_cast<float *>(ws);
-    int rc = g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, nullptr, 0, Y, ldy, P, plan, st);
+    int rc = g2_fused_once<Q, ACT>(W, N, K, X, M, ldx, nullptr, 0, Y, ldy, P, plan, flags, st);
     if (rc != GGUFB200_OK) return rc;
     long long work = M * (N / 8);
     unsigned grid = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
@@ -509,7 +509,7 @@ static int g2_fused_act(const void *W, long long N, long long K, const void *X, 
 
 template <class Q, int ACT>
 static int g2_fused_once(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype,
-                         void *Y, long long ldy, float *partial, G2Plan plan, cudaStream_t st)
+                         void *Y, long long ldy, float *partial, G2Plan plan, int flags, cudaStream_t st)
 {
     CUtensorMap tmA;
     if (!g2_make_map(&tmA, X, M, K, ldx, ACT)) return GGUFB200_E_CUDA;
@@ -525,7 +525,7 @@ static int g2_fused_once(const void *W, long long N, long long K, const void *X,
     constexpr int SEG = PackedSeg<Q>::value;
     if constexpr (SEG > 0) {
         // stage the packed rows through shared memory when a 2-D tensor map over the raw bytes is legal
-        if (g_fused_staged && K % kG2Span == 0 && p.row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+        if (!(flags & kG2Unstaged) && K % kG2Span == 0 && p.row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
             G2EncodeFn fn = g2_encode_fn();
             if (!fn) return GGUFB200_E_CUDA;
             CUtensorMap tmW;
@@ -547,13 +547,14 @@ static int g2_fused_once(const void *W, long long N, long long K, const void *X,
 }
 
 int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype,
-                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, cudaStream_t st)
+                         int math_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes, int flags,
+                         cudaStream_t st)
 {
     if (math_dtype != kF16 || K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
 #define GGUFB200_G2_CASE(T)                                                                                               \
     case T:                                                                                                               \
-        return act_dtype == kBF16 ? g2_fused_act<Block<T>, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, st)  \
-                                  : g2_fused_act<Block<T>, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, st);
+        return act_dtype == kBF16 ? g2_fused_act<Block<T>, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags, st)  \
+                                  : g2_fused_act<Block<T>, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags, st);
     switch (type) {
         GGUFB200_G2_CASE(T_Q4_0)
         GGUFB200_G2_CASE(T_Q4_1)
@@ -570,26 +571,6 @@ int gemm2_fused_dispatch(int type, const void *W, long long N, long long K, cons
     }
 #undef GGUFB200_G2_CASE
     return GGUFB200_E_UNSUPPORTED;
-}
-
-int gemm2_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act_dtype,
-                         const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
-{
-    if (K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
-    CUtensorMap tmA, tmB;
-    if (!g2_make_map(&tmA, X, M, K, ldx, act_dtype)) return GGUFB200_E_CUDA;
-    if (!g2_make_map(&tmB, W, N, K, ldw, act_dtype)) return GGUFB200_E_CUDA;
-    Gemm2Params p{};
-    p.M = M; p.N = N; p.K = K;
-    p.bias = bias; p.bias_dtype = bias_dtype;
-    p.Y = reinterpret_cast<uint8_t *>(Y); p.ldy = ldy;
-    const int accs = g2_pick_accs(M, N);
-    if (act_dtype == kBF16) {
-        if (accs == 2) return g2_launch<void, kF16, kBF16, 2>(tmA, tmB, p, st);
-        return g2_launch<void, kF16, kBF16, 1>(tmA, tmB, p, st);
-    }
-    if (accs == 2) return g2_launch<void, kF16, kF16, 2>(tmA, tmB, p, st);
-    return g2_launch<void, kF16, kF16, 1>(tmA, tmB, p, st);
 }
 
 }  // namespace ggufb200

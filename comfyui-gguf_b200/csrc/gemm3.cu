@@ -65,7 +65,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1;
     const int n_pairs = gridDim.x >> 1;
-    const int num_kb = (int)(p.K / kG2BK);
+    const int num_kb = (int)((p.K + kG2BK - 1) / kG2BK);   // a ragged last k-block is zero-filled by the TMA engine on both operands
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kG3Stages; ++s) {
@@ -222,7 +222,7 @@ static int g3_launch(const CUtensorMap &tmA, const CUtensorMap &tmB, Gemm3Params
 int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw, const void *X, long long M, long long ldx, int act_dtype,
                          const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st)
 {
-    if (K % kG2BK != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
+    if (K % 8 != 0 || N % 8 != 0) return GGUFB200_E_UNSUPPORTED;
     const int sms = sm_count();
     const long long tiles256 = ((M + 255) / 256) * ((N + 255) / 256);
     const bool narrow = tiles256 <= sms / 4;       // far fewer 256-wide tiles than SM pairs: halve the tile width

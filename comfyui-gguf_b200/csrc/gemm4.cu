@@ -1,0 +1,592 @@
+// gemm4.cu -- K2/K3 v2: persistent fused dequant -> TENSOR MEMORY -> tcgen05 Linear (the default fused route).
+//
+//   Y[M,N] = X[M,K] * dequant(W)[N,K]^T (+ bias)      X fp16 / bf16, W packed GGUF blocks, fp32 accumulation in TMEM
+//
+// The product is computed TRANSPOSED:  D[feature n, token m] = sum_k W[n,k] * X[m,k],  i.e. the dequantised weight is the
+// A operand of the UMMA and the activations are the B operand.  tcgen05.mma can read A from tensor memory, so the dequant
+// warps write their fp16 results with tcgen05.st straight into TMEM columns and W never touches shared memory: the
+// shared-memory port, which bounds both the smem-fed fused kernel (gemm2.cu: A by TMA + B by STS + UMMA reads of both
+// = 119 B/clk of 128) and the dense kernel, only carries the activation tiles (TMA write + UMMA read, <= 64 B/clk) and the
+// packed bytes (0.56 B/element).  kind::f16 takes A = f16 with B = bf16, so bf16 activations need no fp16 -> bf16
+// conversion of W either.
+//
+// Cluster = 2 CTAs, tcgen05.mma.cta_group::2: UMMA M = 256 features (128 TMEM lanes per CTA), N = TT tokens.
+//   TMEM (512 columns per CTA):  [0, 2*TT) two accumulator slots of TT fp32 columns,  [A_BASE, A_BASE + 32*AST) ring of
+//   AST A-operand stages, one stage = this CTA's 128 features x 64 k as fp16 pairs (32 columns).
+//   ACCS = 1: an item is one TT-token tile, the slots alternate between items (epilogue of item i overlaps the main loop
+//             of item i+1).   ACCS = 2: an item is 2*TT tokens, both slots are fed from the same A stage (each dequantised
+//             element feeds twice the flops; the epilogue is not overlapped).
+// Persistent: grid = min(#SM pairs, #items) clusters, item = (K range, feature tile, token tile), token tile fastest.
+// Warp roles per CTA (768 threads):
+//   0      TMA producer, activations: X tile [ACCS x TT/2 tokens x 64 k] per k-block, 128B-swizzled, bytes of both CTAs are
+//          credited to the leader's full_x barrier (.cta_group::2)
+//   1      MMA issuer (leader CTA, one thread)
+//   2      TMEM allocation; relay: forwards "this CTA's A stage is complete" to the leader with one cluster-scope arrive
+//   3      TMA producer, packed weight: this CTA's 128 rows of one 256-wide K-span per copy (2-D tensor map over the raw
+//          bytes, or one bulk copy from the re-packed span-major layout), ring of NP buffers
+//   4-7    epilogue: TMEM -> registers -> (+bias, cast) -> global, one warp per TMEM lane quadrant
+//   8-23   dequant producers: group g = (warp-8)/4 owns the k-blocks with kb % 4 == g, warp quadrant = warp % 4, lane = feature
+//          row; a thread unpacks 64 consecutive k of its row (produce.cuh) and stores them with two tcgen05.st.32x32b.x16
+// K is processed in whole 256-wide spans: a ragged tail (K % 256 != 0) is zero-filled by the TMA engine on both operands.
+#include <type_traits>
+
+#include "produce.cuh"
+#include "umma.cuh"
+
+namespace ggufb200 {
+
+constexpr int kG4Threads = 768;
+constexpr int kG4EpiWarp0 = 4;
+constexpr int kG4ProdWarp0 = 8;
+
+template <int TT> struct G4Tmem {
+    static constexpr int A_BASE = ((2 * TT + 31) / 32) * 32;
+    static constexpr int AST_RAW = (512 - A_BASE) / 32;
+    static constexpr int AST = AST_RAW >= 12 ? 12 : (AST_RAW / 4) * 4;      // a multiple of 4: group g owns stages == g (mod 4)
+    static_assert(AST >= 4, "token tile too wide for the A ring");
+};
+
+template <int SPAN_BYTES, int TT, int ACCS> struct G4Cfg {
+    static constexpr int X_BYTES = (TT / 2) * 128;                 // one X sub-tile of this CTA: TT/2 tokens x 64 k x 2 B
+    static constexpr int XSTAGE = ACCS * X_BYTES;
+    static constexpr int XS = TT >= 128 ? (ACCS == 2 ? 4 : 6) : 8;
+    static constexpr int P_BYTES = (128 * SPAN_BYTES + 1023) & ~1023;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XS * XSTAGE;
+    static constexpr int NP_MAX = TT >= 128 ? 4 : 8;
+    static constexpr int NP = BUDGET / P_BYTES < NP_MAX ? BUDGET / P_BYTES : NP_MAX;
+    static constexpr int SMEM = XS * XSTAGE + NP * P_BYTES + 1024 + 1024;
+    static_assert(NP >= 2, "packed span buffers do not fit");
+    static_assert(X_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+};
+
+struct G4Params {
+    long long M, N, K;
+    const void *bias;
+    int bias_dtype;
+    uint8_t *Y;
+    long long ldy;
+    float *partial;          // split-K: fp32 [splits, M, N]
+    const uint8_t *Wspan;    // re-packed span-major layout (nullptr: 2-D tensor map over the canonical rows)
+    long long span_stride;   // bytes between consecutive spans of the re-packed layout (= padded rows * span bytes)
+    int ttiles, ftiles, splits;
+    int spans_total, spans_per_split;
+    int n_items;
+};
+
+__device__ __forceinline__ void g4_tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void g4_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (A from tensor memory: SASS UTCHMMA.2CTA tmem, gdesc, tmem)
+__device__ __forceinline__ void g4_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// kind::f16 instruction descriptor: D = f32, A = f16 (the dequantised weight), B = activation dtype, both K-major,
+// UMMA M = 256 (pair), N = TT
+template <int ACT, int TT> __device__ __forceinline__ constexpr uint32_t g4_idesc()
+{
+    const uint32_t bfmt = ACT == kBF16 ? 1u : 0u;
+    return (1u << 4) | (0u << 7) | (bfmt << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+struct G4Item {
+    int split, ftile, ttile, span0, nspans;
+};
+__device__ __forceinline__ G4Item g4_item(const G4Params &p, int item)
+{
+    G4Item it;
+    const int per = p.ftiles * p.ttiles;
+    it.split = item / per;
+    const int rem = item - it.split * per;
+    it.ftile = rem / p.ttiles;
+    it.ttile = rem - it.ftile * p.ttiles;
+    it.span0 = it.split * p.spans_per_split;
+    it.nspans = min(p.spans_per_split, p.spans_total - it.span0);
+    return it;
+}
+
+template <class Q, int ACT, int TT, int ACCS, bool FAST>
+__global__ void __launch_bounds__(kG4Threads, 1)
+gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const G4Params p)
+{
+    constexpr int SPAN = SpanOf<Q>::BYTES;
+    using Cfg = G4Cfg<SPAN, TT, ACCS>;
+    using TM = G4Tmem<TT>;
+    using Prod = typename std::conditional<FAST, FastProducer<Q>, Producer<Q>>::type;
+    constexpr int XS = Cfg::XS, NP = Cfg::NP, AST = TM::AST;
+
+    extern __shared__ uint8_t g4_smem_raw[];
+    uint8_t *xt = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(g4_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *packed = xt + XS * Cfg::XSTAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(packed + NP * Cfg::P_BYTES);
+    uint64_t *full_x = bars;                     // [XS]  leader's copy collects both CTAs' TMA bytes
+    uint64_t *empty_x = full_x + XS;             // [XS]  multicast tcgen05.commit
+    uint64_t *full_p = empty_x + XS;             // [NP]  packed span landed (local)
+    uint64_t *empty_p = full_p + NP;             // [NP]  16 producer warps are done with the span (local)
+    uint64_t *full_a = empty_p + NP;             // [AST] local: the 4 warps of the owning group stored their quadrants
+    uint64_t *full_a2 = full_a + AST;            // [AST] leader's copy: one relay arrive per CTA
+    uint64_t *empty_a = full_a2 + AST;           // [AST] multicast tcgen05.commit
+    uint64_t *tmem_full = empty_a + AST;         // [2]   multicast tcgen05.commit
+    uint64_t *tmem_empty = tmem_full + 2;        // [2]   leader's copy: one arrive per epilogue thread of both CTAs
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    static_assert((2 * XS + 2 * NP + 3 * AST + 4) * 8 + 8 <= 1024, "barrier block");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < XS; ++s) {
+            mbar_init(&full_x[s], 1);
+            mbar_init(&empty_x[s], 1);
+        }
+        for (int s = 0; s < NP; ++s) {
+            mbar_init(&full_p[s], 1);
+            mbar_init(&empty_p[s], 16);
+        }
+        for (int s = 0; s < AST; ++s) {
+            mbar_init(&full_a[s], 4);
+            mbar_init(&full_a2[s], 2);
+            mbar_init(&empty_a[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 2 * 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    g2_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    g2_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: activation tiles
+        if (lane == 0) {
+            int it = 0;
+            for (int item = pair; item < p.n_items; item += n_pairs) {
+                const G4Item w = g4_item(p, item);
+                const int m0 = w.ttile * (TT * ACCS) + (int)rank * (TT / 2);
+                const int kb0 = w.span0 * 4, nkb = w.nspans * 4;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % XS;
+                    mbar_wait(&empty_x[s], (uint32_t)(((it / XS) & 1) ^ 1));
+                    uint8_t *dst = xt + s * Cfg::XSTAGE;
+                    const uint32_t bar = mapa_u32(smem_u32(&full_x[s]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full_x[s], 2 * Cfg::XSTAGE);
+#pragma unroll
+                    for (int a = 0; a < ACCS; ++a) tma_load_2d_pair(dst + a * Cfg::X_BYTES, &tmX, bar, (kb0 + kb) * kG2BK, m0 + a * TT);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA producer: packed weight spans of this CTA's 128 feature rows
+        if (lane == 0) {
+            int sp = 0;
+            for (int item = pair; item < p.n_items; item += n_pairs) {
+                const G4Item w = g4_item(p, item);
+                const int n0 = w.ftile * 256 + (int)rank * 128;
+                for (int i = 0; i < w.nspans; ++i, ++sp) {
+                    const int b = sp % NP;
+                    mbar_wait(&empty_p[b], (uint32_t)(((sp / NP) & 1) ^ 1));
+                    mbar_arrive_expect_tx(&full_p[b], 128 * SPAN);
+                    if (p.Wspan) {
+                        bulk_g2s(packed + b * Cfg::P_BYTES, p.Wspan + (long long)(w.span0 + i) * p.span_stride + (long long)n0 * SPAN, 128 * SPAN,
+                                 &full_p[b]);
+                    } else {
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                                smem_u32(packed + b * Cfg::P_BYTES)),
+                            "l"(reinterpret_cast<uint64_t>(&tmW)), "r"(smem_u32(&full_p[b])), "r"((w.span0 + i) * (SPAN > 256 ? SPAN / 2 : SPAN)),
+                            "r"(n0)
+                            : "memory");
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one thread)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = g4_idesc<ACT, TT>();
+            int it = 0, ti = 0;
+            for (int item = pair; item < p.n_items; item += n_pairs, ++ti) {
+                const G4Item w = g4_item(p, item);
+                const int nkb = w.nspans * 4;
+                // accumulator slot(s) of this item must have been drained by the epilogue
+                if constexpr (ACCS == 1) {
+                    mbar_wait_cluster(&tmem_empty[ti & 1], (uint32_t)(((ti >> 1) & 1) ^ 1));
+                } else {
+                    mbar_wait_cluster(&tmem_empty[0], (uint32_t)((ti & 1) ^ 1));
+                    mbar_wait_cluster(&tmem_empty[1], (uint32_t)((ti & 1) ^ 1));
+                }
+                g2_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int sx = it % XS, sa = it % AST;
+                    mbar_wait_cluster(&full_x[sx], (uint32_t)((it / XS) & 1));
+                    mbar_wait_cluster(&full_a2[sa], (uint32_t)((it / AST) & 1));
+                    g2_fence_after();
+                    const uint32_t x_addr = smem_u32(xt + sx * Cfg::XSTAGE);
+                    const uint32_t a_col = tmem_base + (uint32_t)(TM::A_BASE + sa * 32);
+#pragma unroll
+                    for (int j = 0; j < kG2BK / 16; ++j) {
+#pragma unroll
+                        for (int a = 0; a < ACCS; ++a) {
+                            const int slot = ACCS == 1 ? (ti & 1) : a;
+                            g4_umma_ts(tmem_base + (uint32_t)(slot * TT), a_col + (uint32_t)(j * 8),
+                                       g2_desc_sw128(x_addr + a * Cfg::X_BYTES + j * 32), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit_pair(&empty_x[sx]);
+                    umma_commit_pair(&empty_a[sa]);
+                }
+                if constexpr (ACCS == 1) {
+                    umma_commit_pair(&tmem_full[ti & 1]);
+                } else {
+                    umma_commit_pair(&tmem_full[0]);
+                    umma_commit_pair(&tmem_full[1]);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== relay: this CTA's A stage is complete -> one cluster-scope arrive on the leader's barrier
+        if (lane == 0) {
+            int it = 0;
+            for (int item = pair; item < p.n_items; item += n_pairs) {
+                const G4Item w = g4_item(p, item);
+                const int nkb = w.nspans * 4;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int sa = it % AST;
+                    mbar_wait(&full_a[sa], (uint32_t)((it / AST) & 1));
+                    g2_fence_after();
+                    g2_fence_before();
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&full_a2[sa]), 0));
+                }
+            }
+        }
+    } else if (warp >= kG4ProdWarp0) {
+        // ===================== dequant producers: packed span (smem) -> fp16 pairs -> tensor memory
+        const int g = (warp - kG4ProdWarp0) >> 2;            // k-block owner group 0..3
+        const int quad = warp & 3;                           // TMEM lane quadrant of this warp
+        const int row = quad * 32 + lane;                    // feature row inside this CTA's 128
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TM::A_BASE;
+        int sp = 0, itg = 0;                                 // spans seen; k-blocks this group has produced
+        for (int item = pair; item < p.n_items; item += n_pairs) {
+            const G4Item w = g4_item(p, item);
+            for (int i = 0; i < w.nspans; ++i, ++sp, ++itg) {
+                const int b = sp % NP;
+                const int it = 4 * itg + g;                  // global k-block index of this group's quarter of the span
+                const int sa = it % AST;
+                mbar_wait(&full_p[b], (uint32_t)((sp / NP) & 1));
+                mbar_wait(&empty_a[sa], (uint32_t)(((it / AST) & 1) ^ 1));
+                g2_fence_after();
+                const uint8_t *src = packed + b * Cfg::P_BYTES + row * SPAN;
+                const uint32_t taddr = lane_base + (uint32_t)(sa * 32);
+                Prod::run64(src, g, [&](int half, const uint32_t (&o)[16]) { g4_tmem_st16(taddr + (uint32_t)(half * 16), o); });
+                g4_tmem_st_wait();
+                g2_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&full_a[sa]);
+                    mbar_arrive(&empty_p[b]);
+                }
+            }
+        }
+    } else if (warp >= kG4EpiWarp0) {
+        // ===================== epilogue: D[feature (lane), token (column)] -> Y[token, feature]
+        const int quad = warp & 3;
+        const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+        const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+        const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        int ti = 0;
+        for (int item = pair; item < p.n_items; item += n_pairs, ++ti) {
+            const G4Item w = g4_item(p, item);
+            const long long n = (long long)w.ftile * 256 + rank * 128 + quad * 32 + lane;      // this thread's feature
+            const bool n_ok = n < p.N;
+            float bv = 0.f;
+            if (p.bias && n_ok && !p.partial) bv = g2_bias<ACT>(p.bias, p.bias_dtype, n);
+#pragma unroll 1
+            for (int a = 0; a < ACCS; ++a) {
+                const int slot = ACCS == 1 ? (ti & 1) : a;
+                const uint32_t par = ACCS == 1 ? (uint32_t)((ti >> 1) & 1) : (uint32_t)(ti & 1);
+                mbar_wait_cluster(&tmem_full[slot], par);
+                g2_fence_after();
+                const long long m_base = (long long)w.ttile * (TT * ACCS) + a * TT;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TT; c0 += 32) {
+                    uint32_t r[32];
+                    g2_tmem_ld32(tmem_base + lane_sel + (uint32_t)(slot * TT + c0), r);
+                    g2_tmem_ld_wait();
+                    if (p.partial) {
+                        float *dst = p.partial + ((long long)w.split * p.M + m_base + c0) * p.N + n;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n_ok && m_base + c0 + j < p.M) dst[(long long)j * p.N] = __uint_as_float(r[j]);
+                    } else {
+                        uint16_t *dst = reinterpret_cast<uint16_t *>(p.Y) + (m_base + c0) * p.ldy + n;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]) + bv;
+                            uint16_t hb;
+                            if constexpr (ACT == kBF16) hb = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+                            else hb = __half_as_ushort(__float2half_rn(v));
+                            if (n_ok && m_base + c0 + j < p.M) dst[(long long)j * p.ldy] = hb;
+                        }
+                    }
+                }
+                g2_fence_before();
+                mbar_arrive_cluster(slot ? empty_remote1 : empty_remote0);
+            }
+        }
+    }
+
+    g2_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        g2_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+struct G4Plan {
+    int tt, accs, splits, spans_per_split, ttiles, ftiles, n_items;
+};
+
+// Tiling: token tile TT in {32, 128, 192}; ACCS = 2 (384-token items) when asked for; K split into ranges of whole spans
+// when the output has fewer items than SM pairs (short activations; every packed byte is still read exactly once).
+static G4Plan g4_plan(long long M, long long N, long long K, size_t ws_bytes, int want_accs, bool allow_split = true)
+{
+    G4Plan pl{};
+    const int pairs = sm_count() / 2;
+    pl.ftiles = (int)((N + 255) / 256);
+    pl.accs = 1;
+    if (M <= 32) pl.tt = 32;
+    else if (M <= 128 || (M <= 1024 && (M + 127) / 128 * 128 < (M + 191) / 192 * 192)) pl.tt = 128;
+    else pl.tt = 192;
+    if (pl.tt == 192 && want_accs == 2 && M > 192) pl.accs = 2;
+    const int tile_tokens = pl.tt * pl.accs;
+    pl.ttiles = (int)((M + tile_tokens - 1) / tile_tokens);
+    const int spans = (int)((K + 255) / 256);
+    const long long tiles = (long long)pl.ftiles * pl.ttiles;
+    int s = 1;
+    const size_t slice = (size_t)M * (size_t)N * 4;
+    if (allow_split && tiles < pairs && slice > 0 && ws_bytes >= 2 * slice) {
+        long long want = pairs / tiles;
+        if (want > spans) want = spans;
+        if (want > 32) want = 32;
+        if (want > (long long)(ws_bytes / slice)) want = (long long)(ws_bytes / slice);
+        if (want >= 2) s = (int)want;
+    }
+    pl.spans_per_split = (spans + s - 1) / s;
+    pl.splits = (spans + pl.spans_per_split - 1) / pl.spans_per_split;
+    pl.n_items = (int)(tiles * pl.splits);
+    return pl;
+}
+
+constexpr size_t kG4SplitWsCap = 64u << 20;
+
+// flags: bit 1 (2) = 384-token items, bit 2 (4) = no split-K
+size_t gemm4_workspace(long long M, long long N, long long K, int flags)
+{
+    const G4Plan pl = g4_plan(M, N, K, kG4SplitWsCap, (flags & 2) ? 2 : 1, !(flags & 4));
+    return pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * 4 : 0;
+}
+
+void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items)
+{
+    const G4Plan pl = g4_plan(M, N, K, ws_bytes > kG4SplitWsCap ? kG4SplitWsCap : ws_bytes, (flags & 2) ? 2 : 1, !(flags & 4));
+    *tile_tokens = pl.tt * pl.accs;
+    *splits = pl.splits;
+    *spans_per_split = pl.spans_per_split;
+    *items = pl.n_items;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256) g4_finalize_kernel(const float *__restrict__ P, int splits, const void *__restrict__ bias, int bias_dtype,
+                                                          uint8_t *__restrict__ Y, long long M, long long N, long long ldy)
+{
+    // Y = act(sum_s P[s] + bias), slices added in ascending order (bit-reproducible)
+    const long long n8 = N / 8;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < M * n8; i += (long long)gridDim.x * 256) {
+        const long long m = i / n8, n = (i % n8) * 8;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int sp = 0; sp < splits; ++sp) {
+            const float *src = P + ((long long)sp * M + m) * N + n;
+            const float4 a = *reinterpret_cast<const float4 *>(src), b = *reinterpret_cast<const float4 *>(src + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += g2_bias<ACT>(bias, bias_dtype, n + j);
+        }
+        st_global_v4(Y + (m * ldy + n) * 2, g2_pack<ACT>(v[0], v[1]), g2_pack<ACT>(v[2], v[3]), g2_pack<ACT>(v[4], v[5]), g2_pack<ACT>(v[6], v[7]));
+    }
+}
+
+struct G4Args {
+    const void *W;             // canonical packed rows
+    const void *Wspan;         // re-packed span-major layout or nullptr
+    long long span_stride;
+    long long N, K;
+    const void *X;
+    long long M, ldx;
+    const void *bias;
+    int bias_dtype;
+    void *Y;
+    long long ldy;
+    void *ws;
+    size_t ws_bytes;
+    int fast, want_accs, nosplit;
+    cudaStream_t st;
+};
+
+template <class Q, int ACT, int TT, int ACCS, bool FAST>
+static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
+{
+    constexpr int SPAN = SpanOf<Q>::BYTES;
+    using Cfg = G4Cfg<SPAN, TT, ACCS>;
+    auto kern = gemm4_kernel<Q, ACT, TT, ACCS, FAST>;
+    static unsigned char attr[64] = {};
+    if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
+    G2EncodeFn fn = g2_encode_fn();
+    if (!fn) return GGUFB200_E_CUDA;
+    CUtensorMap tmX, tmW;
+    if (!g2_make_map(&tmX, a.X, a.M, a.K, a.ldx, ACT, TT / 2)) return GGUFB200_E_CUDA;
+    const long long row_bytes = a.K / Q::BS * Q::TS;
+    if (a.Wspan) {
+        tmW = tmX;   // unused by the kernel in this mode
+    } else {
+        const bool wide = SPAN > 256;     // inner box extent is limited to 256 elements: use 2-byte elements
+        cuuint64_t dims[2] = {(cuuint64_t)(wide ? row_bytes / 2 : row_bytes), (cuuint64_t)a.N};
+        cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+        cuuint32_t box[2] = {(cuuint32_t)(wide ? SPAN / 2 : SPAN), 128u};
+        cuuint32_t estr[2] = {1, 1};
+        if (fn(&tmW, wide ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(a.W), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return GGUFB200_E_CUDA;
+    }
+    G4Params p{};
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.bias = partial ? nullptr : a.bias;
+    p.bias_dtype = a.bias_dtype;
+    p.Y = reinterpret_cast<uint8_t *>(a.Y);
+    p.ldy = a.ldy;
+    p.partial = partial;
+    p.Wspan = reinterpret_cast<const uint8_t *>(a.Wspan);
+    p.span_stride = a.span_stride;
+    p.ttiles = pl.ttiles; p.ftiles = pl.ftiles; p.splits = pl.splits;
+    p.spans_total = (int)((a.K + 255) / 256);
+    p.spans_per_split = pl.spans_per_split;
+    p.n_items = pl.n_items;
+    int pairs = sm_count() / 2;
+    if (pairs > p.n_items) pairs = p.n_items;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kG4Threads);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = a.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <class Q, int ACT, bool FAST> static int g4_tiles(const G4Args &a, const G4Plan &pl, float *partial)
+{
+    if (pl.tt == 32) return g4_launch<Q, ACT, 32, 1, FAST>(a, pl, partial);
+    if (pl.tt == 128) return g4_launch<Q, ACT, 128, 1, FAST>(a, pl, partial);
+    if (pl.accs == 2) return g4_launch<Q, ACT, 192, 2, FAST>(a, pl, partial);
+    return g4_launch<Q, ACT, 192, 1, FAST>(a, pl, partial);
+}
+
+template <class Q, int ACT> static int g4_run(const G4Args &a)
+{
+    const bool ws_ok = a.ws && (reinterpret_cast<uintptr_t>(a.ws) & 15) == 0;
+    size_t wsb = ws_ok ? a.ws_bytes : 0;
+    if (wsb > kG4SplitWsCap) wsb = kG4SplitWsCap;
+    const G4Plan pl = g4_plan(a.M, a.N, a.K, wsb, a.want_accs, !a.nosplit);
+    float *partial = pl.splits > 1 ? reinterpret_cast<float *>(a.ws) : nullptr;
+    int rc;
+    if (a.fast && FastProducer<Q>::fast) rc = g4_tiles<Q, ACT, true>(a, pl, partial);
+    else rc = g4_tiles<Q, ACT, false>(a, pl, partial);
+    if (rc != GGUFB200_OK || !partial) return rc;
+    const long long work = a.M * (a.N / 8);
+    const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
+    g4_finalize_kernel<ACT><<<grid, 256, 0, a.st>>>(partial, pl.splits, a.bias, a.bias_dtype, reinterpret_cast<uint8_t *>(a.Y), a.M, a.N, a.ldy);
+    return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+// The canonical packed layout can be staged by a 2-D tensor map when one row's span and the row stride are multiples of 16 B
+template <class Q> static bool g4_canonical_ok(const void *W, long long K)
+{
+    const long long row_bytes = K / Q::BS * Q::TS;
+    return SpanOf<Q>::BYTES % 16 == 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+}
+
+// flags: bit 0 = fast producers (single-FMA float step), bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K
+int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
+                         long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
+                         int flags, cudaStream_t st)
+{
+    if (N % 8 != 0 || K % 8 != 0) return GGUFB200_E_UNSUPPORTED;
+    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags & 1, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0, st};
+#define GGUFB200_G4_CASE(T)                                                                    \
+    case T:                                                                                    \
+        if (!Wspan && !g4_canonical_ok<Block<T>>(W, K)) return GGUFB200_E_UNSUPPORTED;         \
+        return act_dtype == kBF16 ? g4_run<Block<T>, kBF16>(a) : g4_run<Block<T>, kF16>(a);
+    switch (type) {
+        GGUFB200_G4_CASE(T_Q4_0)
+        GGUFB200_G4_CASE(T_Q4_1)
+        GGUFB200_G4_CASE(T_Q5_0)
+        GGUFB200_G4_CASE(T_Q5_1)
+        GGUFB200_G4_CASE(T_Q8_0)
+        GGUFB200_G4_CASE(T_Q4_K)
+        GGUFB200_G4_CASE(T_Q5_K)
+        GGUFB200_G4_CASE(T_IQ4_NL)
+    }
+#undef GGUFB200_G4_CASE
+    return GGUFB200_E_UNSUPPORTED;
+}
+
+bool gemm4_supported(int type, const void *W, long long N, long long K)
+{
+    if (N % 8 != 0 || K % 8 != 0) return false;
+    switch (type) {
+    case T_Q4_0: return g4_canonical_ok<Block<T_Q4_0>>(W, K);
+    case T_Q4_1: return g4_canonical_ok<Block<T_Q4_1>>(W, K);
+    case T_Q5_0: return g4_canonical_ok<Block<T_Q5_0>>(W, K);
+    case T_Q5_1: return g4_canonical_ok<Block<T_Q5_1>>(W, K);
+    case T_Q8_0: return g4_canonical_ok<Block<T_Q8_0>>(W, K);
+    case T_Q4_K: return g4_canonical_ok<Block<T_Q4_K>>(W, K);
+    case T_Q5_K: return g4_canonical_ok<Block<T_Q5_K>>(W, K);
+    case T_IQ4_NL: return g4_canonical_ok<Block<T_IQ4_NL>>(W, K);
+    }
+    return false;
+}
+
+}  // namespace ggufb200

@@ -1,4 +1,4 @@
-// gemv.cu -- K3: small-M fused dequant + dot product  Y[m,n] = sum_k X[m,k] * W[n,k] (+bias).
+// gemv.cu -- K3 (reference-exact W): small-M fused dequant + dot product  Y[m,n] = sum_k X[m,k] * W[n,k] (+bias).
 //
 // For M <= 8 (modulation / adaLN / time-embedding Linears at batch 1..8) the Linear is bound by
 // reading the PACKED weight once from HBM; the weight is never materialised.  One warp owns an
@@ -14,7 +14,6 @@ constexpr int kGemvThreads = 256;
 constexpr int kGemvMaxM = 8;
 
 int gemv_max_m() { return kGemvMaxM; }
-int g_gemv_mma = 1;   // ggufb200_set_tuning(5, v): 1 = mma.sync tile kernel (default), 0 = warp-per-row FMA kernel
 
 template <int ACT> __device__ __forceinline__ float2 act_bits_to_f32x2(uint32_t b)
 {
@@ -32,66 +31,6 @@ template <int ACT> __device__ __forceinline__ float load_bias(const void *bias, 
     else b = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(bias)[n]);
     if constexpr (ACT == kBF16) return __bfloat162float(__float2bfloat16_rn(b));
     else return __half2float(__float2half_rn(b));
-}
-
-template <class Q, int MATH, int ACT, int MM>
-__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const uint8_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
-                                                            long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
-                                                            uint8_t *__restrict__ Y, long long ldy)
-{
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * kGemvThreads + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * kGemvThreads) >> 5;
-    const long long row_bytes = K / Q::BS * Q::TS;
-
-    for (long long n = warp; n < N; n += n_warps) {
-        const uint8_t *wrow = W + n * row_bytes;
-        float acc[MM];
-#pragma unroll
-        for (int m = 0; m < MM; ++m) acc[m] = 0.0f;
-
-        // one lane = runs of 32 consecutive k: the block header / sub-block scales are decoded once per run
-        constexpr int GROUP = GroupOf<Q>::value;
-        for (long long k = lane * 32; k < K; k += 1024) {
-            const uint8_t *blk = wrow + (k / Q::BS) * Q::TS;
-            const int e0 = (int)(k % Q::BS);
-            const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
-            GroupScale<MATH> g1 = g0;
-            if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                typename Math<MATH>::T2 v[4];
-                dequant_elems<Q, MATH, 8>(blk, e0 + c * 8, (GROUP == 16 && c >= 2) ? g1 : g0, v);
-                float2 w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = act_bits_to_f32x2<ACT>(pack16<ACT, MATH>(v[j]));
-#pragma unroll
-                for (int m = 0; m < MM; ++m) {
-                    if (m < M) {
-                        const uint4 xv = *reinterpret_cast<const uint4 *>(X + ((long long)m * ldx + k + c * 8) * 2);
-                        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float2 xf = act_bits_to_f32x2<ACT>(xs[j]);
-                            acc[m] = fmaf(w[j].x, xf.x, acc[m]);
-                            acc[m] = fmaf(w[j].y, xf.y, acc[m]);
-                        }
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < MM; ++m) {
-            float a = acc[m];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0 && m < M) {
-                if (bias) a += load_bias<ACT>(bias, bias_dtype, n);
-                if constexpr (ACT == kBF16) reinterpret_cast<__nv_bfloat16 *>(Y)[(long long)m * ldy + n] = __float2bfloat16_rn(a);
-                else reinterpret_cast<__half *>(Y)[(long long)m * ldy + n] = __float2half_rn(a);
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------ tensor-core variant (default)
@@ -276,19 +215,12 @@ static int gemv_launch(const void *W, long long N, long long K, const void *X, l
     const uint8_t *w = reinterpret_cast<const uint8_t *>(W);
     const uint8_t *x = reinterpret_cast<const uint8_t *>(X);
     uint8_t *y = reinterpret_cast<uint8_t *>(Y);
-    if (g_gemv_mma && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {   // the 16-byte header / quant loads need an aligned base
-        long long tiles = (N + 15) / 16;
-        const int sms = sm_count();
-        long long cap = (long long)sms * 8;
-        unsigned g = (unsigned)(tiles < cap ? tiles : cap);
-        gemv_mma_kernel<Q, MATH, ACT><<<g, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
-        return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
-    }
-    unsigned grid = gemv_grid(N);
-    if (M <= 1) gemv_kernel<Q, MATH, ACT, 1><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
-    else if (M <= 2) gemv_kernel<Q, MATH, ACT, 2><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
-    else if (M <= 4) gemv_kernel<Q, MATH, ACT, 4><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
-    else gemv_kernel<Q, MATH, ACT, 8><<<grid, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
+    if ((reinterpret_cast<uintptr_t>(W) & 15) != 0) return GGUFB200_E_ALIGN;   // the 16-byte header / quant loads need an aligned base
+    long long tiles = (N + 15) / 16;
+    const int sms = sm_count();
+    long long cap = (long long)sms * 8;
+    unsigned g = (unsigned)(tiles < cap ? tiles : cap);
+    gemv_mma_kernel<Q, MATH, ACT><<<g, kGemvThreads, 0, st>>>(w, N, K, x, ldx, (int)M, bias, bias_dtype, y, ldy);
     return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 

@@ -137,14 +137,11 @@ def _launch_linear(x, wraw, qtype, N, K, bias, math, algo):
         bias_ptr, bias_code = bias.data_ptr(), dtype_code(bias.dtype)
     w_ptr = wraw.data_ptr()
     if w_ptr & 15:
-        algo = _lib.ALGO_DEQUANT_MMA      # byte-offset view: only the standalone dequant stages arbitrary alignment
-    elif algo == _lib.ALGO_AUTO and M > GEMV_MAX_M and math != _F16_CODE:
-        algo = _lib.ALGO_DEQUANT_MMA      # the fused tensor-core producer is fp16-math only; size the workspace accordingly
+        algo = _lib.ALGO_DEQUANT_MMA | (algo & ~_lib.ALGO_MASK)   # byte-offset view: only the standalone dequant stages any alignment
     L = _lib.lib()
     qcode = int(qtype)
     ws, ws_ptr = None, None
-    gemv = M <= GEMV_MAX_M and algo == _lib.ALGO_AUTO          # the small-M kernel needs no scratch: skip the query
-    need = 0 if gemv else L.ggufb200_linear_workspace(qcode, M, N, K, act, algo)
+    need = L.ggufb200_linear_workspace_ex(qcode, M, N, K, act, math, algo)     # same routing function as the call below
     if need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
         ws_ptr = ws.data_ptr()
@@ -162,7 +159,7 @@ def _launch_linear(x, wraw, qtype, N, K, bias, math, algo):
 
 
 def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
-    """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.
+    """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.  `algo` = _lib.ALGO_* | _lib.FLAG_*.
 
     x: CUDA fp16/bf16 [..., K]; weight: CUDA GGMLTensor (quantised type); bias: None or a CUDA tensor
     (fp32 / fp16 / bf16, rounded to x.dtype inside the kernel exactly like ops.py:205-207 does)."""
@@ -355,6 +352,12 @@ class GGMLOps(comfy_ops.manual_cast):
         # tests/test_gpu_linear.py); set to False to get the reference's two-step arithmetic back.
         lora_side_gemm = True
 
+        # Numerics contract of the packed-weight Linear (include/ggufb200.h GGUFB200_FLAG_EXACT_W):
+        #   "fast"   (default) AUTO may take the TMEM-fed fused kernel: integer unpack bit-exact, one fused multiply-add per
+        #            element for the hot formats, fp16 W fed to the tensor core without the cast to bf16
+        #   "exact"  only routes whose weight operand is bit-identical to the reference's `dequantize_tensor(...).to(dtype)`
+        linear_numerics = "fast"
+
         def _fused_ok(self, input):
             w = self.weight
             return (input.is_cuda and input.dtype in _FUSED_ACT and is_quantized(w)
@@ -412,10 +415,11 @@ class GGMLOps(comfy_ops.manual_cast):
                 if M < 0:
                     pass                                               # feature mismatch: let F.linear raise the usual error
                 elif qtype == _Q.BF16 and M > GEMV_MAX_M:
-                    if input.dtype == torch.bfloat16 and K % 64 == 0:  # already dense: straight to the tensor-core GEMM
+                    if input.dtype == torch.bfloat16 and K % 8 == 0 and N % 8 == 0:   # already dense: straight to the tensor-core GEMM
                         y = linear_dense(input, wraw.view(torch.bfloat16).view(N, K), b)
-                elif M <= GEMV_MAX_M or (K % 64 == 0 and N % 8 == 0):
-                    y = _launch_linear(input, wraw, qtype, N, K, b, math_code(self.dequant_dtype, input.dtype), _lib.ALGO_AUTO)
+                elif M <= GEMV_MAX_M or N % 8 == 0:                    # (the M <= 8 kernel stores per element: any N)
+                    algo = _lib.ALGO_AUTO if self.linear_numerics == "fast" else _lib.ALGO_AUTO | _lib.FLAG_EXACT_W
+                    y = _launch_linear(input, wraw, qtype, N, K, b, math_code(self.dequant_dtype, input.dtype), algo)
                 if y is not None:
                     return self._add_lora(y, input, terms) if terms else y
             weight, bias = self.cast_bias_weight(input)

@@ -11,7 +11,10 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the
  *     caller (PyTorch); the library never allocates, frees or retains device memory
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream)
- *   - all calls are asynchronous on `stream`, re-entrant and hold no mutable global state
+ *   - all calls are asynchronous on `stream` and re-entrant; routing depends only on the arguments of the call
+ *     (the library keeps no mutable routing state; ggufb200_set_tuning() is a benchmark-only switch that is refused
+ *     unless the process opted in with GGUFB200_ALLOW_TUNING=1)
+ *   - the device code is sm_100a only: calls that would launch a kernel return GGUFB200_E_DEVICE on any other GPU
  *   - return value: 0 = GGUFB200_OK, negative = error (ggufb200_strerror()); no C++
  *     exception crosses the boundary
  *   - ggml_type uses gguf-py's GGMLQuantizationType integer values
@@ -29,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GGUFB200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define GGUFB200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 /* error codes */
 #define GGUFB200_OK 0
@@ -54,11 +57,31 @@ extern "C" {
 #define GGUFB200_OP_ROWS 2
 #define GGUFB200_OP_LINEAR_MMA 3 /* large-M tcgen05 path (fused or dequant+GEMM) available for this type */
 
-/* algorithm selector for ggufb200_linear() */
+/* algorithm selector for ggufb200_linear(): one GGUFB200_ALGO_* value, optionally OR-ed with GGUFB200_FLAG_* bits */
 #define GGUFB200_ALGO_AUTO 0
-#define GGUFB200_ALGO_GEMV 1        /* small-M fused dequant + dot product (CUDA cores, HBM-read bound) */
-#define GGUFB200_ALGO_FUSED_MMA 2   /* fused dequant -> smem -> tcgen05.mma, accumulators in TMEM */
-#define GGUFB200_ALGO_DEQUANT_MMA 3 /* dequant into the caller's workspace, then the tcgen05 GEMM on it */
+#define GGUFB200_ALGO_GEMV 1        /* M <= 8: fused dequant + mma.sync dot products, W bit-identical to the reference */
+#define GGUFB200_ALGO_FUSED_MMA 2   /* fused dequant -> shared memory -> tcgen05.mma (W bit-identical to the reference) */
+#define GGUFB200_ALGO_DEQUANT_MMA 3 /* dequant into the caller's workspace, then the tcgen05 GEMM on it (W bit-identical) */
+#define GGUFB200_ALGO_FUSED_TMEM 4  /* fused dequant -> TENSOR MEMORY -> tcgen05.mma, any M (persistent; the AUTO default) */
+#define GGUFB200_ALGO_MASK 0xFF
+
+/* Per-call switches (no process-wide state):
+ *   EXACT_W    AUTO only picks routes whose weight operand is bit-identical to what the reference hands to F.linear
+ *              (dequant.py float sequence with per-op rounding, then the cast to the activation dtype).  Without it AUTO
+ *              prefers GGUFB200_ALGO_FUSED_TMEM, whose contract is: integer unpack bit-exact; sub-block scale products
+ *              as the reference; the per-element float step is ONE fused multiply-add in fp16 (hot formats) and the fp16
+ *              weight is fed to the tensor core unrounded (no cast of W to bf16) -- the result is at least as close to
+ *              the exact product as the reference's and within 1e-3 (fp16) / 8e-3 (bf16, = the same bound in bf16 ulps)
+ *              of it.
+ *   GENERIC    FUSED_TMEM: use the reference-rounding producers instead of the hand-written ones
+ *   TILE384    FUSED_TMEM: 384-token items (both accumulator slots per dequantised tile, epilogue not overlapped)
+ *   NOSPLIT    FUSED_MMA / FUSED_TMEM: never cut K into ranges
+ *   UNSTAGED   FUSED_MMA: producers read packed rows from global memory instead of TMA-staged shared memory */
+#define GGUFB200_FLAG_EXACT_W 0x100
+#define GGUFB200_FLAG_GENERIC 0x200
+#define GGUFB200_FLAG_TILE384 0x400
+#define GGUFB200_FLAG_NOSPLIT 0x800
+#define GGUFB200_FLAG_UNSTAGED 0x1000
 
 int ggufb200_version(void);
 const char *ggufb200_strerror(int rc);
@@ -107,20 +130,25 @@ int ggufb200_dequant_rows(int ggml_type, const void *packed, int64_t n_table_row
  * -> get_weight/dequantize_tensor (ops.py:166-191) -> F.linear.
  *   W_packed    N rows of K/block_size*type_size bytes (loader.py:118-120 layout)
  *   X, Y        act_dtype (0 fp16 / 1 bf16), row strides ldx / ldy in ELEMENTS, 16-byte aligned
- *   math_dtype  as in ggufb200_dequant(): W is first produced in math_dtype with the
- *               reference's rounding sequence and then cast to act_dtype, exactly the
- *               weight the reference hands to F.linear; accumulation is fp32
+ *   math_dtype  as in ggufb200_dequant().  Routes 1-3: W is first produced in math_dtype with the reference's rounding
+ *               sequence and then cast to act_dtype, exactly the weight the reference hands to F.linear.  Route 4
+ *               (GGUFB200_ALGO_FUSED_TMEM, fp16 math only) follows the contract under GGUFB200_FLAG_EXACT_W above.
+ *               Accumulation is fp32 on every route.
  *   bias        NULL or N values of bias_dtype (0/1/2)
  *   workspace   scratch of at least ggufb200_linear_workspace() bytes (may be NULL if that is 0).  A W_packed that is
  *               not 16-byte aligned is always served by GGUFB200_ALGO_DEQUANT_MMA and needs that algo's workspace.
  *               GGUFB200_ALGO_FUSED_MMA with few output tiles (short M) cuts K into S ranges across SM pairs and keeps
  *               the fp32 partial results in the workspace (S*M*N*4 bytes, summed in a fixed order: reproducible);
- *               with less room it uses fewer ranges, with none it runs unsplit.  The size reported
- *               for GGUFB200_ALGO_AUTO assumes math_dtype == fp16 (the reference default); with another math dtype
- *               query and pass GGUFB200_ALGO_DEQUANT_MMA.
- *   algo        GGUFB200_ALGO_*
+ *               with less room it uses fewer ranges, with none it runs unsplit; GGUFB200_ALGO_FUSED_TMEM likewise.
+ *               ggufb200_linear_workspace() assumes math_dtype == fp16 (the reference default);
+ *               ggufb200_linear_workspace_ex() takes the math dtype of the call.
+ *   algo        GGUFB200_ALGO_* | GGUFB200_FLAG_*
  */
 size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int algo);
+
+/* Same query with the math dtype of the call: GGUFB200_ALGO_AUTO routes a non-fp16 math dtype to
+ * GGUFB200_ALGO_DEQUANT_MMA, and this variant reports that route's size (query and call always agree). */
+size_t ggufb200_linear_workspace_ex(int ggml_type, int64_t M, int64_t N, int64_t K, int act_dtype, int math_dtype, int algo);
 
 int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M,
                     int64_t ldx, int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y,
@@ -134,20 +162,19 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
 int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *X, int64_t M, int64_t ldx,
                   int act_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *stream);
 
-/* Diagnostics: the tiling GGUFB200_ALGO_FUSED_MMA uses for this problem when given `workspace_bytes` of scratch --
- * activation rows per SM-pair tile (256 or 512), number of K ranges (1 = unsplit), 64-wide k-blocks per range (the last
- * range may be shorter, never empty) and the number of CTAs launched.  Pure host arithmetic, no GPU needed. */
-int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int *tile_rows, int *k_ranges,
+/* Diagnostics: the tiling a fused kernel uses for this problem when given `workspace_bytes` of scratch.
+ * algo = GGUFB200_ALGO_FUSED_MMA (| flags): activation rows per SM-pair tile (256 or 512), number of K ranges (1 = unsplit),
+ *   64-wide k-blocks per range (the last range may be shorter, never empty), CTAs launched.
+ * algo = GGUFB200_ALGO_FUSED_TMEM (| flags): tokens per item (32 / 128 / 192 / 384), number of K ranges, k-blocks per range,
+ *   number of work items (persistent grid = min(items, SM pairs) clusters).
+ * Pure host arithmetic, no GPU needed. */
+int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int algo, int *tile_rows, int *k_ranges,
                          int *kblocks_per_range, int *ctas);
 
-/* Tuning knobs for benchmarks (process-wide, read-mostly): key 0 = dequant CTAs per SM (0 = default),
- * key 1 = programmatic dependent launch of the dequant kernel (default 1),
- * key 2 = tensor-core GEMM variant: 2 = CTA-pair UMMA + persistent double-buffered dense GEMM (default),
- *         1 = CTA-pair UMMA (cta_group::2), 0 = single-CTA UMMA,
- * key 3 = large-M route chosen by GGUFB200_ALGO_AUTO: 0 = dequant + GEMM (default, needs the workspace), 1 = fused,
- * key 4 = fused kernel stages the packed rows through shared memory with TMA when legal (default 1),
- * key 5 = small-M kernel: 1 = mma.sync tile kernel (default), 0 = warp-per-row FMA kernel,
- * key 6 = split-K of the fused kernel when the output has fewer tiles than SM pairs (default 1). */
+/* Benchmark-only launch knobs of the standalone dequant kernel (they never change routing or results):
+ * key 0 = dequant CTAs per SM (0 = default), key 1 = programmatic dependent launch (default 1).
+ * Refused with GGUFB200_E_UNSUPPORTED unless the environment variable GGUFB200_ALLOW_TUNING=1 is set when the
+ * library is first used; every other key is refused always (route selection is per call: GGUFB200_ALGO_* | GGUFB200_FLAG_*). */
 int ggufb200_set_tuning(int key, int value);
 
 #ifdef __cplusplus

@@ -2,7 +2,9 @@
 // (comfyui-gguf_b200/csrc/blocks.cuh, common.cuh -- the very code the CUDA kernels inline) on the CPU, so that
 // `pytest -m "not gpu"` can compare the device arithmetic bit for bit with the oracle (oracle/gguf_oracle.c), which in turn
 // is pinned to the unmodified reference (dequant.py:61-285).  Nothing in the product links or loads this file.
-#include "../comfyui-gguf_b200/csrc/blocks.cuh"
+#include <type_traits>
+
+#include "../comfyui-gguf_b200/csrc/produce.cuh"
 
 using namespace ggufb200;
 
@@ -67,6 +69,20 @@ template <class Q, int ACT> int run_fast16(const uint8_t *blocks, long long n_bl
     }
 }
 
+// W producers of the TMEM-fed fused kernel (produce.cuh): spans of `span_bytes` per row, 16-byte aligned, rows of
+// 256 elements; out: fp16 bit patterns, n_spans * 256 elements
+template <class Q, bool FAST> int run_produce(const uint8_t *spans, long long n_spans, int pitch, uint16_t *out)
+{
+    using P = typename std::conditional<FAST, FastProducer<Q>, Producer<Q>>::type;
+    for (long long s = 0; s < n_spans; ++s)
+        for (int kq = 0; kq < 4; ++kq)
+            P::run64(spans + s * pitch, kq, [&](int half, const uint32_t (&o)[16]) {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(out + s * 256 + kq * 64 + half * 32);
+                for (int j = 0; j < 16; ++j) dst[j] = o[j];
+            });
+    return 0;
+}
+
 }  // namespace
 
 #define HOSTF_TYPES(X) X(T_Q4_0) X(T_Q4_1) X(T_Q5_0) X(T_Q5_1) X(T_Q8_0) X(T_Q2_K) X(T_Q3_K) X(T_Q4_K) X(T_Q5_K) X(T_Q6_K) X(T_IQ4_NL) X(T_IQ4_XS)
@@ -89,6 +105,19 @@ int hostf_fast16(int type, const uint8_t *blocks, long long n_blocks, uint32_t *
 {
     switch (type) {
 #define X(T) case T: return act_dtype == kBF16 ? run_fast16<Block<T>, kBF16>(blocks, n_blocks, out) : run_fast16<Block<T>, kF16>(blocks, n_blocks, out);
+        HOSTF_TYPES(X)
+#undef X
+    }
+    return -1;
+}
+
+// produce.cuh: fast != 0 selects FastProducer<Q> (falls back to the generic one for formats without a hand-written producer).
+// Returns 1 when the fast request was served by a hand-written producer, 0 when by the generic one.
+int hostf_produce(int type, const uint8_t *spans, long long n_spans, int pitch, uint16_t *out, int fast)
+{
+    switch (type) {
+#define X(T) case T: if (fast) { run_produce<Block<T>, true>(spans, n_spans, pitch, out); return FastProducer<Block<T>>::fast ? 1 : 0; } \
+                     run_produce<Block<T>, false>(spans, n_spans, pitch, out); return 0;
         HOSTF_TYPES(X)
 #undef X
     }

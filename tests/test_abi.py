@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(pkg):
 
 def test_version_and_strerror(pkg):
     L = pkg.lib.lib()
-    assert L.ggufb200_version() == 100
+    assert L.ggufb200_version() == 200
     assert L.ggufb200_strerror(0) == b"ok"
     for rc in range(-9, 0):
         assert len(L.ggufb200_strerror(rc)) > 3
@@ -72,12 +72,12 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
         pkg.lib.lib()
 
 
-def test_tuning_keys_and_gemm_validation_without_gpu(pkg):
+def test_tuning_is_refused_and_gemm_validation_without_gpu(pkg):
     L = pkg.lib.lib()
-    for key, value in ((0, 4), (1, 1), (2, 2), (3, 0), (4, 1), (5, 1), (6, 1)):
-        assert L.ggufb200_set_tuning(key, value) == 0
-    assert L.ggufb200_set_tuning(99, 1) == -8                      # unknown knob
-    L.ggufb200_set_tuning(0, 0)
+    # route selection is per call (algo | flags); the process-wide knobs are gone, the two launch knobs of the dequant kernel
+    # are benchmark-only and need GGUFB200_ALLOW_TUNING=1 in the environment (not set in the test process)
+    for key in (0, 1, 2, 3, 4, 5, 6, 99):
+        assert L.ggufb200_set_tuning(key, 1) == -8
     buf = (ctypes.c_uint8 * 4096)()
     p16 = (ctypes.addressof(buf) + 15) & ~15
     # ggufb200_gemm: dtype must be 16-bit, leading dimensions >= K and multiples of 8, pointers aligned
@@ -87,17 +87,39 @@ def test_tuning_keys_and_gemm_validation_without_gpu(pkg):
     assert L.ggufb200_gemm(p16, 8, 64, 64, p16, 0, 64, 1, None, 0, p16, 8, None) == 0   # M == 0 is a no-op
     # ggufb200_linear: an unaligned packed weight needs the dequant+GEMM workspace
     assert L.ggufb200_linear(int(Q.Q4_K), p16 + 2, 8, 256, p16, 4, 256, 1, 0, None, 0, p16, 8, None, 0, 0, None) == -3
-    # workspace contract (no GPU needed): dequant+GEMM wants the dense weight, the fused kernel its split-K accumulation buffer
+
+
+def test_workspace_contract_follows_the_route(pkg):
+    """Workspace query == what the call with the same (algo | flags, math dtype) will use; no GPU needed."""
+    L = pkg.lib.lib()
+    A = pkg.lib
     q4k = int(Q.Q4_K)
-    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 3) == 3072 * 3072 * 2      # ALGO_DEQUANT_MMA
-    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 2) == 0                    # FUSED, enough tiles
-    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 2) == 16 * 64 * 512 * 4       # FUSED, split-K: 16 slices
-    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 0) == 16 * 64 * 512 * 4       # AUTO picks split-K fused
-    assert L.ggufb200_linear_workspace(q4k, 512, 3072, 12288, 1, 2) == 6 * 512 * 3072 * 4   # 12 tiles of 512x256 -> 6 ranges
-    assert L.ggufb200_linear_workspace(q4k, 4608, 3072, 3072, 1, 0) == 3072 * 3072 * 2      # AUTO picks dequant+GEMM
-    assert L.ggufb200_linear_workspace(q4k, 4, 3072, 3072, 1, 0) == 0                       # GEMV
-    L.ggufb200_set_tuning(6, 0)
-    assert L.ggufb200_linear_workspace(q4k, 64, 512, 4096, 1, 2) == 0
-    L.ggufb200_set_tuning(6, 1)
+    ws = L.ggufb200_linear_workspace
+    assert ws(q4k, 4608, 3072, 3072, 1, A.ALGO_DEQUANT_MMA) == 3072 * 3072 * 2
+    assert ws(q4k, 4608, 3072, 3072, 1, A.ALGO_FUSED_MMA) == 0                        # enough tiles: unsplit
+    assert ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_MMA) == 16 * 64 * 512 * 4           # split-K: 16 slices
+    assert ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_MMA | A.FLAG_NOSPLIT) == 0
+    assert ws(q4k, 512, 3072, 12288, 1, A.ALGO_FUSED_MMA) == 6 * 512 * 3072 * 4       # 12 tiles of 512x256 -> 6 ranges
+    # AUTO, default contract: the TMEM-fed fused kernel for every M (K ranges only when items < SM pairs)
+    assert ws(q4k, 4608, 3072, 3072, 1, A.ALGO_AUTO) == 0
+    assert ws(q4k, 4, 3072, 3072, 1, A.ALGO_AUTO) == 6 * 4 * 3072 * 4
+    assert ws(q4k, 4, 18432, 3072, 1, A.ALGO_AUTO) == 0
+    assert ws(q4k, 64, 512, 4096, 1, A.ALGO_AUTO) == ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_TMEM) == 16 * 64 * 512 * 4
+    # AUTO restricted to reference-exact weights: GEMV / split-K fused / dequant+GEMM as in round 1
+    ex = A.ALGO_AUTO | A.FLAG_EXACT_W
+    assert ws(q4k, 4608, 3072, 3072, 1, ex) == 3072 * 3072 * 2
+    assert ws(q4k, 64, 512, 4096, 1, ex) == 16 * 64 * 512 * 4
+    assert ws(q4k, 4, 3072, 3072, 1, ex) == 0
+    # a non-fp16 math dtype always means the reference's own sequence in that dtype: dequant + GEMM above the GEMV range
+    wx = L.ggufb200_linear_workspace_ex
+    assert wx(q4k, 4608, 3072, 3072, 1, 1, A.ALGO_AUTO) == 3072 * 3072 * 2
+    assert wx(q4k, 64, 512, 4096, 1, 2, A.ALGO_AUTO) == 512 * 4096 * 2
+    assert wx(q4k, 4, 3072, 3072, 1, 2, A.ALGO_AUTO) == 0
+    assert wx(q4k, 64, 512, 4096, 1, 0, A.ALGO_AUTO) == ws(q4k, 64, 512, 4096, 1, A.ALGO_AUTO)
+    # formats / shapes the TMEM route cannot stage from the canonical rows fall back to the exact routes
+    assert ws(int(Q.Q6_K), 4608, 3072, 3072, 1, A.ALGO_AUTO) == 3072 * 3072 * 2       # 210-byte blocks
+    assert ws(int(Q.Q8_0), 4608, 7296, 2432, 1, A.ALGO_AUTO) == 7296 * 2432 * 2       # 2584-byte rows
     # row gather: K must be a multiple of the block size
+    buf = (ctypes.c_uint8 * 4096)()
+    p16 = (ctypes.addressof(buf) + 15) & ~15
     assert L.ggufb200_dequant_rows(int(Q.Q4_K), p16, 4, 100, p16, 1, p16, 0, 0, None) == -4

@@ -28,7 +28,7 @@ def hostf():
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    deps = [SRC, os.path.join(CSRC, "blocks.cuh"), os.path.join(CSRC, "common.cuh")]
+    deps = [SRC, os.path.join(CSRC, "blocks.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "produce.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "--expt-relaxed-constexpr",
@@ -36,6 +36,7 @@ def hostf():
     L = ctypes.CDLL(OUT)
     L.hostf_dequant.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     L.hostf_fast16.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int]
+    L.hostf_produce.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     L.hostf_k_scale_min.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.hostf_iq4_lookup4.restype = ctypes.c_uint32
     L.hostf_iq4_lookup4.argtypes = [ctypes.c_uint32]
@@ -179,3 +180,79 @@ def test_functors_never_read_past_the_last_block(tmp_path):
         pytest.skip("sanitizer link not available: " + r.stderr[-200:])
     run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0 and "asan run ok" in run.stdout, run.stderr[-2000:]
+
+
+# ---------------------------------------------------------------- produce.cuh: W producers of the TMEM-fed fused kernel
+EXACT_FAST = {Q.Q8_0, Q.Q4_0, Q.Q6_K}          # hand-written producers whose float step already has a single rounding
+FMA_FAST = {Q.Q4_K, Q.Q5_K}                    # one fused multiply-add instead of multiply + subtract
+
+
+def _spans(qt, n_spans, seed, wild=False, pitch=None):
+    """n_spans spans of 256 elements; returns (aligned byte view with row pitch `pitch`, canonical [n_spans, span_bytes])."""
+    bs, ts = oracle.type_info(int(qt))
+    span = 256 // bs * ts
+    if wild:
+        raw = np.random.default_rng(seed).integers(0, 256, size=n_spans * span, dtype=np.uint8)
+    else:
+        raw = oracle.random_blocks(int(qt), n_spans * 256 // bs, seed=seed, scale=0.02).reshape(-1)
+    raw = raw.reshape(n_spans, span)
+    pitch = pitch or span
+    padded = np.zeros((n_spans, pitch), dtype=np.uint8)
+    padded[:, :span] = raw
+    return _aligned_copy(padded), raw, pitch
+
+
+@pytest.mark.parametrize("qt", TYPES, ids=lambda q: q.name)
+@pytest.mark.parametrize("wild", [False, True], ids=["trained-like", "raw-bytes"])
+def test_generic_producer_is_the_reference_fp16_weight(hostf, qt, wild):
+    """Producer<Q> (every format): bit-identical to the reference's fp16 dequant (dequant.py, dequant_dtype=None)."""
+    n = 600
+    bs, ts = oracle.type_info(int(qt))
+    span = 256 // bs * ts
+    pitch = (span + 15) // 16 * 16                     # rows of the staged layout start on 16-byte boundaries
+    buf, raw, pitch = _spans(qt, n, seed=int(qt) + 1, wild=wild, pitch=pitch)
+    got = np.empty(n * 256, dtype=np.uint16)
+    assert hostf.hostf_produce(int(qt), buf.ctypes.data, n, pitch, got.ctypes.data, 0) == 0
+    want = oracle.dequant(raw.reshape(-1, ts), int(qt), oracle.DT_F16, oracle.DT_F16)
+    assert _equal_mod_nan(got, want, oracle.DT_F16)
+
+
+@pytest.mark.parametrize("qt", sorted(EXACT_FAST | FMA_FAST, key=int), ids=lambda q: q.name)
+def test_fast_producers(hostf, qt):
+    """FastProducer<Q>: the integer unpack is the reference's; formats whose float step is a single multiply stay
+    bit-exact; Q4_K / Q5_K replace fp16(fp16(D*q) - M) by one fused multiply-add fp16(D*q - M): the correctly rounded
+    value of the float step, which differs from the reference by at most the rounding of its intermediate product
+    (half an ulp of D*q) plus the final roundings, and is at least as close to the exact value D*q - M."""
+    n = 2000
+    bs, ts = oracle.type_info(int(qt))
+    span = 256 // bs * ts
+    pitch = (span + 15) // 16 * 16
+    buf, raw, pitch = _spans(qt, n, seed=int(qt) + 11, pitch=pitch)
+    got = np.empty(n * 256, dtype=np.uint16)
+    assert hostf.hostf_produce(int(qt), buf.ctypes.data, n, pitch, got.ctypes.data, 1) == 1
+    want = oracle.dequant(raw.reshape(-1, ts), int(qt), oracle.DT_F16, oracle.DT_F16)
+    if qt in EXACT_FAST:
+        assert _equal_mod_nan(got, want, oracle.DT_F16)
+        return
+    g, w = got.view(np.float16).astype(np.float64), want.view(np.float16).astype(np.float64)
+    # exact value of the float step with the reference's sub-block products D = fp16(d*sc), M = fp16(dmin*mn)
+    q, sc, mn = oracle.unpack_int(raw.reshape(-1, ts), int(qt))
+    blocks = raw.reshape(-1, ts)
+    d = blocks[:, 0:2].copy().view(np.float16).astype(np.float32)
+    dmin = blocks[:, 2:4].copy().view(np.float16).astype(np.float32)
+    D = (d * sc.reshape(len(blocks), -1).astype(np.float32)).astype(np.float16).astype(np.float64)
+    Mm = (dmin * mn.reshape(len(blocks), -1).astype(np.float32)).astype(np.float16).astype(np.float64)
+    exact = (D * q.reshape(len(blocks), -1) - Mm).reshape(-1)
+    assert np.array_equal(got.view(np.float16), exact.astype(np.float16))                 # = one correctly rounded FMA
+    assert np.abs(g - exact).sum() <= np.abs(w - exact).sum()
+    prod = np.abs(D * q.reshape(len(blocks), -1)).reshape(-1)
+    bound = 0.5 * np.spacing(prod.astype(np.float16)).astype(np.float64) + np.spacing(np.maximum(np.abs(g), np.abs(w)).astype(np.float16)).astype(np.float64)
+    assert np.all(np.abs(g - w) <= bound)
+
+
+def test_fast_request_falls_back_to_generic_for_other_formats(hostf):
+    buf, raw, pitch = _spans(Q.Q3_K, 8, seed=1, pitch=112)
+    got = np.empty(8 * 256, dtype=np.uint16)
+    assert hostf.hostf_produce(int(Q.Q3_K), buf.ctypes.data, 8, pitch, got.ctypes.data, 1) == 0
+    want = oracle.dequant(raw.reshape(-1, 110), int(Q.Q3_K), oracle.DT_F16, oracle.DT_F16)
+    assert _equal_mod_nan(got, want, oracle.DT_F16)

@@ -15,9 +15,12 @@ PAIRS = 74          # 148 SMs (sm_count() reports 148 without a device as well)
 CAP = 64 << 20
 
 
-def _plan(L, qt, M, N, K, ws):
+FUSED_MMA, FUSED_TMEM, NOSPLIT, TILE384 = 2, 4, 0x800, 0x400
+
+
+def _plan(L, qt, M, N, K, ws, algo=FUSED_MMA):
     vals = [ctypes.c_int() for _ in range(4)]
-    rc = L.ggufb200_linear_plan(int(qt), M, N, K, ws, *[ctypes.byref(v) for v in vals])
+    rc = L.ggufb200_linear_plan(int(qt), M, N, K, ws, algo, *[ctypes.byref(v) for v in vals])
     return rc, tuple(v.value for v in vals)
 
 
@@ -42,7 +45,6 @@ def _check(L, M, N, K, ws):
 
 def test_known_plans(pkg):
     L = pkg.lib.lib()
-    L.ggufb200_set_tuning(2, 2), L.ggufb200_set_tuning(6, 1)
     assert _plan(L, Q.Q4_K, 512, 3072, 12288, CAP) == (0, (512, 6, 32, 144))      # the ncu'd launch: 12 tiles x 6 ranges
     assert _plan(L, Q.Q5_K, 512, 4096, 4096, CAP) == (0, (512, 4, 16, 128))        # T5 q/k/v/o
     assert _plan(L, Q.Q4_K, 4608, 3072, 3072, CAP)[1][1] == 1                      # plenty of tiles: unsplit
@@ -71,11 +73,55 @@ def test_plan_invariants(pkg, M, n8, k64, ws_slices):
     assert ranges <= max(1, need // (M * N * 4))
 
 
-def test_split_knob_disables_every_split(pkg):
+def test_nosplit_flag_disables_every_split(pkg):
     L = pkg.lib.lib()
-    L.ggufb200_set_tuning(6, 0)
-    try:
-        for M, N, K in ((64, 512, 4096), (512, 3072, 12288), (1000, 256, 5120)):
-            assert _plan(L, Q.Q4_K, M, N, K, CAP)[1][1] == 1
-    finally:
-        L.ggufb200_set_tuning(6, 1)
+    for M, N, K in ((64, 512, 4096), (512, 3072, 12288), (1000, 256, 5120)):
+        assert _plan(L, Q.Q4_K, M, N, K, CAP, FUSED_MMA | NOSPLIT)[1][1] == 1
+        assert _plan(L, Q.Q4_K, M, N, K, CAP, FUSED_TMEM | NOSPLIT)[1][1] == 1
+        assert L.ggufb200_linear_workspace(int(Q.Q4_K), M, N, K, 1, FUSED_TMEM | NOSPLIT) == 0
+
+
+# ---------------------------------------------------------------- TMEM-fed kernel (csrc/gemm4.cu::g4_plan)
+def _check_tmem(L, M, N, K, ws, flags=0):
+    rc, (tokens, ranges, kb, items) = _plan(L, Q.Q4_K, M, N, K, ws, FUSED_TMEM | flags)
+    assert rc == 0
+    assert tokens in (32, 128, 192, 384) and ranges >= 1 and kb >= 4 and kb % 4 == 0      # whole 256-wide spans
+    spans = -(-K // 256)
+    per = kb // 4
+    assert (ranges - 1) * per < spans <= ranges * per              # no empty K range, exact cover
+    tiles = -(-M // tokens) * -(-N // 256)
+    assert items == tiles * ranges
+    if ranges > 1:
+        assert tiles < PAIRS and ranges <= 32
+        assert ranges * M * N * 4 <= min(ws, CAP)
+    if M <= 32:
+        assert tokens == 32
+    return ranges
+
+
+def test_known_tmem_plans(pkg):
+    L = pkg.lib.lib()
+    assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM) == (0, (192, 1, 48, 48 * 24))      # Flux mlp.0: 1152 items
+    assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM | TILE384) == (0, (384, 1, 48, 48 * 12))
+    assert _plan(L, Q.Q4_K, 1, 18432, 3072, CAP, FUSED_TMEM) == (0, (32, 1, 48, 72))               # modulation GEMV: one item per pair
+    assert _plan(L, Q.Q4_K, 1, 3072, 3072, CAP, FUSED_TMEM) == (0, (32, 6, 8, 72))                 # 12 feature tiles x 6 K ranges
+    assert _plan(L, Q.Q4_K, 1, 3072, 3072, 0, FUSED_TMEM)[1][1] == 1                               # no workspace: unsplit
+    assert _plan(L, Q.Q5_K, 512, 4096, 4096, CAP, FUSED_TMEM) == (0, (128, 1, 64, 64))             # T5 q/k/v/o at 512 tokens
+    assert _plan(L, Q.BF16, 64, 512, 4096, CAP, FUSED_TMEM)[0] == -8
+
+
+@settings(max_examples=400, deadline=None)
+@given(M=st.integers(1, 5000), n8=st.integers(1, 3000), k64=st.integers(1, 300), ws_slices=st.integers(0, 40), t384=st.booleans())
+def test_tmem_plan_invariants(pkg, M, n8, k64, ws_slices, t384):
+    L = pkg.lib.lib()
+    N, K = 8 * n8, 64 * k64
+    flags = TILE384 if t384 else 0
+    ws = min(ws_slices * M * N * 4, 1 << 40)
+    ranges = _check_tmem(L, M, N, K, ws, flags)
+    need = L.ggufb200_linear_workspace(int(Q.Q4_K), M, N, K, 1, FUSED_TMEM | flags)
+    assert need % (M * N * 4) == 0 and need <= CAP
+    if need:
+        assert _check_tmem(L, M, N, K, need, flags) == need // (M * N * 4) >= 2
+    else:
+        assert _check_tmem(L, M, N, K, CAP, flags) == 1
+    assert ranges <= max(1, need // (M * N * 4))

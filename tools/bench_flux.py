@@ -32,10 +32,45 @@ def time_steps(fn, steps, warmup):
     return float(np.median(ts)), float(np.min(ts))
 
 
-def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", fused=False,
+class LinearTimer:
+    """CUDA-event pairs around every quantised GGMLOps.Linear forward of one step: GPU time spent inside the Linear layers
+    (kernels + the launch gaps between a layer's own kernels) -- `linear_ms`; the rest of the step is `other_ms`."""
+
+    def __init__(self, ops_mod):
+        self.cls = ops_mod.GGMLOps.Linear
+        self.pairs = []
+
+    def __enter__(self):
+        orig = self.cls.forward_ggml_cast_weights
+        pairs = self.pairs
+
+        def timed(mod, x):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            y = orig(mod, x)
+            b.record()
+            pairs.append((a, b))
+            return y
+        self.orig = orig
+        self.cls.forward_ggml_cast_weights = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.cls.forward_ggml_cast_weights = self.orig
+
+    def total_ms(self):
+        torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self.pairs)), len(self.pairs)
+
+
+ROUTE_NAMES = {"fast": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent)",
+               "exact": "reference-exact routes: GEMV / split-K fused / dequant kernel + tcgen05 GEMM"}
+
+
+def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", numerics="fast",
         block_qtype="Q4_K", batch=1):
     ops_mod, lib = ge._sub("ops"), ge._sub("_lib")
-    lib.lib().ggufb200_set_tuning(3, 1 if fused else 0)
+    ops_mod.GGMLOps.Linear.linear_numerics = numerics
     dev = torch.device(device)
     qt = fh.Q[block_qtype]
     with torch.no_grad():
@@ -55,6 +90,13 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
         finite = bool(torch.isfinite(y_ours).all().item())
         ms_ours, min_ours = time_steps(lambda: ours(**inp), steps, warmup)
         ms_ref, min_ref = time_steps(lambda: ref(**inp), ref_steps, 1) if ref_steps > 0 else (None, None)
+        with LinearTimer(ops_mod) as lt:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ours(**inp)
+            b.record()
+            linear_ms, n_linear = lt.total_ms()
+            timed_step_ms = a.elapsed_time(b)
     flops = fh.linear_flops(ours, img_tokens, txt_tokens, batch)
     return {
         "workload": f"Flux.1-dev-shape DiT ({depth} double + {depth_single} single blocks), block Linears {block_qtype}, others BF16, "
@@ -64,7 +106,9 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
         "speedup_vs_reference_chain": (ms_ref / ms_ours) if ms_ref else None,
         "linear_tflops_per_step": flops / 1e12, "linear_tflops_rate": flops / (ms_ours * 1e-3) / 1e12,
         "packed_weight_gb": packed_bytes / 1e9, "output_rel_err_vs_reference_chain": rel, "output_finite": finite,
-        "large_m_route": "fused dequant+tcgen05" if fused else "dequant kernel + tcgen05 GEMM (CTA pair)",
+        "linear_ms": linear_ms, "other_ms": timed_step_ms - linear_ms, "instrumented_step_ms": timed_step_ms, "quantised_linear_calls": n_linear,
+        "linear_tflops_rate_inside_linears": flops / (linear_ms * 1e-3) / 1e12,
+        "numerics": numerics, "large_m_route": ROUTE_NAMES[numerics],
     }
 
 
@@ -75,7 +119,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--txt", type=int, default=512)
-    ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--numerics", default="fast", choices=["fast", "exact"])
     ap.add_argument("--qtype", default="Q4_K")
     a = ap.parse_args()
-    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, fused=a.fused, block_qtype=a.qtype)))
+    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype)))

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""GPU-side time of the small-M fused Linear (K3): raw C-ABI launches (no Python wrapper work in the loop), weights rotated
-through > L2 worth of buffers, both GEMV kernels.  Prints GB/s of packed weight read vs the HBM peak."""
+"""GPU-side time of the small-M fused Linear (K3): raw C-ABI launches replayed from a CUDA graph (no Python / launch
+overhead in the number), weights rotated through > L2 worth of buffers.  Routes: the TMEM-fed fused kernel (AUTO default,
+32-token items, K ranges across SM pairs) and the reference-exact mma.sync GEMV.  Prints GB/s of packed weight read vs the
+measured HBM peak."""
 import json
 import os
 import sys
@@ -21,11 +23,12 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-st = torch.cuda.current_stream().cuda_stream
-for qname in (sys.argv[1:] or ["Q4_K", "Q8_0"]):
+ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_generic", lib.ALGO_FUSED_TMEM | lib.FLAG_GENERIC), ("gemv_exact", lib.ALGO_GEMV))
+side = torch.cuda.Stream()
+for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
     qt = gguf.GGMLQuantizationType[qname]
     bs, ts = gguf.GGML_QUANT_SIZES[qt]
-    for (N, K) in ((18432, 3072), (9216, 3072)):
+    for (N, K) in ((18432, 3072), (9216, 3072), (3072, 3072)):
         copies = 6
         ws = []
         for c in range(copies):
@@ -35,23 +38,32 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0"]):
         for M in (1, 4, 8):
             x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-            for variant in (1, 0):
-                L.ggufb200_set_tuning(5, variant)
+            for name, algo in ROUTES:
+                need = L.ggufb200_linear_workspace(int(qt), M, N, K, 1, algo)
+                wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
 
-                def launch(i):
-                    rc = L.ggufb200_linear(int(qt), ws[i % copies].data_ptr(), N, K, x.data_ptr(), M, K, 1, 0, None, 0, y.data_ptr(), N, None, 0, 1, st)
+                def launch(i, st):
+                    rc = L.ggufb200_linear(int(qt), ws[i % copies].data_ptr(), N, K, x.data_ptr(), M, K, 1, 0, None, 0, y.data_ptr(), N,
+                                           wsb.data_ptr(), need, algo, st)
                     assert rc == 0, rc
-                for i in range(10):
-                    launch(i)
+                st0 = torch.cuda.current_stream().cuda_stream
+                for i in range(6):
+                    launch(i, st0)
+                torch.cuda.synchronize()
+                per = 12
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for i in range(per):
+                        launch(i, side.cuda_stream)
+                g.replay()
                 torch.cuda.synchronize()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                iters = 120
+                iters = 10
                 a.record()
-                for i in range(iters):
-                    launch(i)
+                for _ in range(iters):
+                    g.replay()
                 b.record()
                 torch.cuda.synchronize()
-                us = a.elapsed_time(b) / iters * 1e3
+                us = a.elapsed_time(b) / (iters * per) * 1e3
                 gbs = N * K // bs * ts / us / 1e3
-                print(f"{qname} N={N} K={K} M={M} {'mma' if variant else 'fma'}: {us:7.1f} us  {gbs:7.1f} GB/s packed read  ({gbs / peak:.3f} of HBM peak)", flush=True)
-L.ggufb200_set_tuning(5, 1)
+                print(f"{qname} N={N} K={K} M={M} {name:12s}: {us:7.1f} us  {gbs:7.1f} GB/s packed read  ({gbs / peak:.3f} of measured HBM peak)", flush=True)
