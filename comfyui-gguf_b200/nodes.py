@@ -6,11 +6,12 @@ package's `GGMLOps`, therefore every quantised Linear that comfy.sd instantiates
 
 The model patcher keeps the one behaviour the hot path relies on (reference nodes.py:43-47): a LoRA on a QUANTISED weight is
 not baked into the packed bytes; the patch list is attached to the tensor (`tensor.patches`) and applied after the dequant on
-every forward.  Dense (F16/F32) weights are patched the usual way.  The reference's mmap-release bounce
-(nodes.py:91-119) is host memory policy and is left to ComfyUI's stock ModelPatcher.load.
+every forward.  Dense (F16/F32) weights are patched the usual way.  `load()` forces `force_patch_weights=True` like the
+reference (nodes.py:94-99): without it a partially loaded (lowvram) module would receive LowVramPatch objects in
+`weight_function`, which the GGUF layers never read, and a LoRA on an offloaded quantised layer would be silently dropped.
+Only the reference's mmap-release bounce (nodes.py:101-119) -- host memory policy -- is left out.
 """
 import collections
-import copy
 import logging
 
 import torch
@@ -89,16 +90,25 @@ class GGUFModelPatcher(comfy.model_patcher.ModelPatcher):
                     param.patches = []
         return super().unpatch_model(device_to=device_to, unpatch_weights=unpatch_weights)
 
+    def load(self, *args, force_patch_weights=False, **kwargs):
+        # quantised layers only understand `tensor.patches`: every patched key must go through patch_weight_to_device,
+        # also for modules that stay on the offload device (reference nodes.py:94-99)
+        return super().load(*args, force_patch_weights=True, **kwargs)
+
     def clone(self, *args, **kwargs):
-        twin = GGUFModelPatcher(self.model, self.load_device, self.offload_device, self.size,
-                                weight_inplace_update=self.weight_inplace_update)
-        twin.patches = {name: list(entries) for name, entries in self.patches.items()}
-        twin.patches_uuid = self.patches_uuid
-        twin.object_patches = self.object_patches.copy()
-        twin.model_options = copy.deepcopy(self.model_options)
-        twin.backup = self.backup
-        twin.object_patches_backup = self.object_patches_backup
+        # The stock clone() copies ALL patcher state (wrappers, callbacks, hooks, attachments, pinned set ...) and builds the
+        # twin with type(self); it is also called unbound on a plain ModelPatcher by the loader nodes (reference
+        # nodes.py:121-132).  Borrow this class for the duration of the base-class clone instead of re-listing its fields.
+        origin = self.__class__
+        self.__class__ = GGUFModelPatcher
+        try:
+            twin = super().clone(*args, **kwargs)
+        finally:
+            self.__class__ = origin
+        twin.__class__ = GGUFModelPatcher
         twin.patch_on_device = getattr(self, "patch_on_device", False)
+        if origin is not GGUFModelPatcher:
+            twin.size = 0          # sized by a foreign patcher class: recompute
         return twin
 
 

@@ -13,6 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a B200: on any other box they are reported as skipped instead of failing in torch.cuda init."""
+    import torch
+    ok = torch.cuda.is_available() and torch.cuda.get_device_capability(0) == (10, 0)
+    if ok:
+        return
+    why = pytest.mark.skip(reason="needs a B200 (sm_100) GPU")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(why)
+
+
 @pytest.fixture(scope="session")
 def pkg():
     import __graft_entry__ as ge
