@@ -63,6 +63,11 @@ def lib() -> ctypes.CDLL:
     L.ggufb200_linear_workspace_ex.argtypes = [c_int, c_i64, c_i64, c_i64, c_int, c_int, c_int]
     L.ggufb200_linear.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_vp, c_i64,
                                   c_vp, c_sz, c_int, c_vp]
+    L.ggufb200_linear_spans.argtypes = [c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_int, c_vp, c_i64,
+                                        c_vp, c_sz, c_int, c_vp]
+    L.ggufb200_repack_bytes.restype = c_sz
+    L.ggufb200_repack_bytes.argtypes = [c_int, c_i64, c_i64]
+    L.ggufb200_repack.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_vp]
     L.ggufb200_gemm.argtypes = [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_vp]
     _lib = L
     return L
@@ -77,4 +82,5 @@ EXPORTS = (
     "ggufb200_version", "ggufb200_strerror", "ggufb200_type_info", "ggufb200_supported", "ggufb200_dequant",
     "ggufb200_unpack_int", "ggufb200_dequant_rows", "ggufb200_linear_workspace", "ggufb200_linear", "ggufb200_gemm",
     "ggufb200_set_tuning", "ggufb200_linear_plan", "ggufb200_linear_workspace_ex",
+    "ggufb200_repack_bytes", "ggufb200_repack", "ggufb200_linear_spans",
 )

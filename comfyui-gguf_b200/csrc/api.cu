@@ -29,6 +29,8 @@ bool gemm4_supported(int type, const void *W, long long N, long long K);
 size_t gemm4_workspace(long long M, long long N, long long K, int flags);
 void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items);
 int gemv_max_m();
+size_t repack_bytes(int type, long long N, long long K, int *pitch, long long *span_stride);
+int repack_dispatch(int type, const void *W, long long N, long long K, void *out, cudaStream_t st);
 }  // namespace ggufb200
 
 using namespace ggufb200;
@@ -120,8 +122,11 @@ static size_t fused_mma_ws(long long M, long long N, long long K, int flags)
     return s > 1 ? (size_t)s * (size_t)M * (size_t)N * 4 : 0;
 }
 
-// `W` may be NULL (workspace query: assume a 16-byte aligned weight); ws_avail = workspace the caller supplied (SIZE_MAX in a query)
-static Route pick_route(int type, const void *W, long long M, long long N, long long K, int act, int math, int algo_flags, size_t ws_avail)
+// `W` may be NULL (workspace query: assume a 16-byte aligned weight); ws_avail = workspace the caller supplied (SIZE_MAX in a query);
+// have_spans: the caller also holds the re-packed span-major copy of the weight (ggufb200_repack), which the TMEM-fed
+// kernel can stage for every block format and every K
+static Route pick_route(int type, const void *W, long long M, long long N, long long K, int act, int math, int algo_flags, size_t ws_avail,
+                        bool have_spans = false)
 {
     const int algo = algo_flags & GGUFB200_ALGO_MASK;
     const int flags = algo_flags & ~GGUFB200_ALGO_MASK;
@@ -132,7 +137,7 @@ static Route pick_route(int type, const void *W, long long M, long long N, long 
     if (algo == GGUFB200_ALGO_AUTO) {
         const bool exact = (flags & GGUFB200_FLAG_EXACT_W) != 0 || math != kF16;
         if (!w_ok) r.algo = GGUFB200_ALGO_DEQUANT_MMA;
-        else if (!exact && fused_type(type) && gemm4_supported(type, W, N, K)) r.algo = GGUFB200_ALGO_FUSED_TMEM;
+        else if (!exact && fused_type(type) && (N % 8) == 0 && (have_spans || gemm4_supported(type, W, N, K))) r.algo = GGUFB200_ALGO_FUSED_TMEM;
         else if (M <= gemv_max_m()) r.algo = GGUFB200_ALGO_GEMV;
         else if (fusable && (exact_prefers_fused(M, N, K) || ws_avail < dense)) r.algo = GGUFB200_ALGO_FUSED_MMA;
         else r.algo = GGUFB200_ALGO_DEQUANT_MMA;
@@ -251,9 +256,9 @@ size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K,
     return ggufb200_linear_workspace_ex(ggml_type, M, N, K, act_dtype, kF16, algo);
 }
 
-int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx, int act_dtype,
-                    int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace, size_t workspace_bytes,
-                    int algo, void *stream)
+static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx,
+                       int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace,
+                       size_t workspace_bytes, int algo, void *stream)
 {
     int bs, ts;
     if (!type_geom(ggml_type, &bs, &ts)) return GGUFB200_E_TYPE;
@@ -273,7 +278,8 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
         if (ws_avail < dense) return GGUFB200_E_ALIGN;
         algo = GGUFB200_ALGO_DEQUANT_MMA | flags;
     }
-    const Route r = pick_route(ggml_type, W_packed, M, N, K, act_dtype, math_dtype, algo, ws_avail);
+    if (W_spans && !aligned16(W_spans)) return GGUFB200_E_ALIGN;
+    const Route r = pick_route(ggml_type, W_packed, M, N, K, act_dtype, math_dtype, algo, ws_avail, W_spans != nullptr);
     // the small-M kernel stores per element: it only needs 2-byte aligned Y rows; every other route moves 16-byte vectors
     const bool vec_y = r.algo != GGUFB200_ALGO_GEMV;
     if (!aligned16(X) || (ldx % 8) != 0) return GGUFB200_E_ALIGN;
@@ -295,8 +301,10 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     }
     case GGUFB200_ALGO_FUSED_TMEM: {
         if (!fused_type(ggml_type) || math_dtype != kF16) return GGUFB200_E_UNSUPPORTED;
-        return gemm4_fused_dispatch(ggml_type, W_packed, nullptr, 0, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, workspace, ws_avail,
-                                    g4_flags(flags), st);
+        long long span_stride = 0;
+        if (W_spans) repack_bytes(ggml_type, N, K, nullptr, &span_stride);
+        return gemm4_fused_dispatch(ggml_type, W_packed, W_spans, span_stride, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, workspace,
+                                    ws_avail, g4_flags(flags), st);
     }
     case GGUFB200_ALGO_DEQUANT_MMA: {
         if (ws_avail < dense) return GGUFB200_E_WORKSPACE;
@@ -306,6 +314,40 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
     }
     }
     return GGUFB200_E_UNSUPPORTED;
+}
+
+int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx, int act_dtype,
+                    int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace, size_t workspace_bytes,
+                    int algo, void *stream)
+{
+    return linear_impl(ggml_type, W_packed, nullptr, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace, workspace_bytes,
+                       algo, stream);
+}
+
+int ggufb200_linear_spans(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx,
+                          int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace,
+                          size_t workspace_bytes, int algo, void *stream)
+{
+    return linear_impl(ggml_type, W_packed, W_spans, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace, workspace_bytes,
+                       algo, stream);
+}
+
+size_t ggufb200_repack_bytes(int ggml_type, int64_t N, int64_t K)
+{
+    int bs;
+    if (!type_geom(ggml_type, &bs, nullptr) || N <= 0 || K <= 0 || K % bs != 0) return 0;
+    return repack_bytes(ggml_type, N, K, nullptr, nullptr);
+}
+
+int ggufb200_repack(int ggml_type, const void *W_packed, int64_t N, int64_t K, void *out, void *stream)
+{
+    int bs;
+    if (!type_geom(ggml_type, &bs, nullptr) || ggml_type == T_BF16) return GGUFB200_E_TYPE;
+    if (N <= 0 || K <= 0 || K % bs != 0) return GGUFB200_E_SHAPE;
+    if (!W_packed || !out) return GGUFB200_E_NULL;
+    if (!aligned16(out) || (reinterpret_cast<uintptr_t>(W_packed) & 1)) return GGUFB200_E_ALIGN;
+    if (int rc = device_check()) return rc;
+    return repack_dispatch(ggml_type, W_packed, N, K, out, (cudaStream_t)stream);
 }
 
 int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int algo, int *tile_rows, int *k_ranges,

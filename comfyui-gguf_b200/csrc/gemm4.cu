@@ -122,8 +122,9 @@ template <class Q, int ACT, int TT, int ACCS, bool FAST>
 __global__ void __launch_bounds__(kG4Threads, 1)
 gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const G4Params p)
 {
-    constexpr int SPAN = SpanOf<Q>::BYTES;
-    using Cfg = G4Cfg<SPAN, TT, ACCS>;
+    constexpr int SPAN = SpanOf<Q>::BYTES;        // packed bytes of one row's K-span (coordinate step of the 2-D tensor map)
+    constexpr int PITCH = SpanOf<Q>::PITCH;       // row pitch of a staged span (== SPAN whenever the 2-D tensor map is legal)
+    using Cfg = G4Cfg<PITCH, TT, ACCS>;
     using TM = G4Tmem<TT>;
     using Prod = typename std::conditional<FAST, FastProducer<Q>, Producer<Q>>::type;
     constexpr int XS = Cfg::XS, NP = Cfg::NP, AST = TM::AST;
@@ -207,9 +208,9 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 for (int i = 0; i < w.nspans; ++i, ++sp) {
                     const int b = sp % NP;
                     mbar_wait(&empty_p[b], (uint32_t)(((sp / NP) & 1) ^ 1));
-                    mbar_arrive_expect_tx(&full_p[b], 128 * SPAN);
+                    mbar_arrive_expect_tx(&full_p[b], 128 * PITCH);
                     if (p.Wspan) {
-                        bulk_g2s(packed + b * Cfg::P_BYTES, p.Wspan + (long long)(w.span0 + i) * p.span_stride + (long long)n0 * SPAN, 128 * SPAN,
+                        bulk_g2s(packed + b * Cfg::P_BYTES, p.Wspan + (long long)(w.span0 + i) * p.span_stride + (long long)n0 * PITCH, 128 * PITCH,
                                  &full_p[b]);
                     } else {
                         asm volatile(
@@ -297,7 +298,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 mbar_wait(&full_p[b], (uint32_t)((sp / NP) & 1));
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / AST) & 1) ^ 1));
                 g2_fence_after();
-                const uint8_t *src = packed + b * Cfg::P_BYTES + row * SPAN;
+                const uint8_t *src = packed + b * Cfg::P_BYTES + row * PITCH;
                 const uint32_t taddr = lane_base + (uint32_t)(sa * 32);
                 Prod::run64(src, g, [&](int half, const uint32_t (&o)[16]) { g4_tmem_st16(taddr + (uint32_t)(half * 16), o); });
                 g4_tmem_st_wait();
@@ -464,7 +465,7 @@ template <class Q, int ACT, int TT, int ACCS, bool FAST>
 static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
 {
     constexpr int SPAN = SpanOf<Q>::BYTES;
-    using Cfg = G4Cfg<SPAN, TT, ACCS>;
+    using Cfg = G4Cfg<SpanOf<Q>::PITCH, TT, ACCS>;
     auto kern = gemm4_kernel<Q, ACT, TT, ACCS, FAST>;
     static unsigned char attr[64] = {};
     if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
@@ -542,6 +543,7 @@ template <class Q, int ACT> static int g4_run(const G4Args &a)
 }
 
 // The canonical packed layout can be staged by a 2-D tensor map when one row's span and the row stride are multiples of 16 B
+// (every other weight needs the re-packed span-major layout of repack.cu)
 template <class Q> static bool g4_canonical_ok(const void *W, long long K)
 {
     const long long row_bytes = K / Q::BS * Q::TS;
@@ -565,9 +567,13 @@ int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long s
         GGUFB200_G4_CASE(T_Q5_0)
         GGUFB200_G4_CASE(T_Q5_1)
         GGUFB200_G4_CASE(T_Q8_0)
+        GGUFB200_G4_CASE(T_Q2_K)
+        GGUFB200_G4_CASE(T_Q3_K)
         GGUFB200_G4_CASE(T_Q4_K)
         GGUFB200_G4_CASE(T_Q5_K)
+        GGUFB200_G4_CASE(T_Q6_K)
         GGUFB200_G4_CASE(T_IQ4_NL)
+        GGUFB200_G4_CASE(T_IQ4_XS)
     }
 #undef GGUFB200_G4_CASE
     return GGUFB200_E_UNSUPPORTED;

@@ -116,7 +116,34 @@ def _is_current_device(index):
 _F16_CODE = _lib.F16
 
 
-def _launch_linear(x, wraw, qtype, N, K, bias, math, algo):
+def needs_span_layout(qtype, K):
+    """True when the canonical GGUF rows cannot be staged by a 2-D tensor map (a row's 256-wide K-span or the row stride is
+    not a multiple of 16 bytes): Q2_K / Q3_K / Q6_K / IQ4_XS always, the others for some K (Q8_0 at K = 2432)."""
+    bs, ts = gguf.GGML_QUANT_SIZES[qtype]
+    return bs > 1 and (((256 // bs) * ts) % 16 != 0 or ((K // bs) * ts) % 16 != 0)
+
+
+def span_layout(weight, wraw):
+    """The re-packed span-major copy of a device-resident packed weight (csrc/repack.cu), built once and
+    cached ON the GGMLTensor object: `.to()` / reload create new tensor objects, so the cache can never outlive its bytes.
+    The canonical bytes are untouched (state_dict / offload semantics stay the reference's)."""
+    key = (wraw.data_ptr(), wraw._version)
+    cached = weight.__dict__.get("_gg_spans")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    qcode = int(weight.tensor_type)
+    N, K = tuple(weight.tensor_shape)
+    L = _lib.lib()
+    nbytes = L.ggufb200_repack_bytes(qcode, N, K)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=wraw.device)
+    with torch.cuda.device(wraw.device):
+        _lib.check(L.ggufb200_repack(qcode, wraw.data_ptr(), N, K, out.data_ptr(), _current_stream_ptr(wraw.device.index)),
+                   f"ggufb200_repack({weight.tensor_type.name}, N={N}, K={K})")
+    weight.__dict__["_gg_spans"] = (key, out)
+    return out
+
+
+def _launch_linear(x, wraw, qtype, N, K, bias, math, algo, spans=None):
     """The call itself.  x: CUDA fp16/bf16 [..., K]; wraw: PLAIN uint8 tensor holding the packed rows on x.device;
     bias: PLAIN tensor on x.device or None.  Kept free of tensor-subclass traffic (every attribute read on a GGMLTensor
     goes through __torch_function__) and of per-call object construction: for short activations the host side of this
@@ -146,28 +173,37 @@ def _launch_linear(x, wraw, qtype, N, K, bias, math, algo):
         ws = torch.empty(need, dtype=torch.uint8, device=device)
         ws_ptr = ws.data_ptr()
     index = device.index
+    if spans is not None:
+        def call():
+            return L.ggufb200_linear_spans(qcode, w_ptr, spans.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code,
+                                           y.data_ptr(), N, ws_ptr, need, algo, _current_stream_ptr(index))
+    else:
+        def call():
+            return L.ggufb200_linear(qcode, w_ptr, N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
+                                     ws_ptr, need, algo, _current_stream_ptr(index))
     if _is_current_device(index):                     # the common case: no device-guard round trip
-        rc = L.ggufb200_linear(qcode, w_ptr, N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
-                               ws_ptr, need, algo, _current_stream_ptr(index))
+        rc = call()
     else:
         with torch.cuda.device(device):
-            rc = L.ggufb200_linear(qcode, w_ptr, N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code, y.data_ptr(), N,
-                                   ws_ptr, need, algo, _current_stream_ptr(index))
+            rc = call()
     if rc:
         _lib.check(rc, f"ggufb200_linear({getattr(qtype, 'name', qtype)}, M={M}, N={N}, K={K})")
     return y if x.dim() == 2 else y.reshape(*x.shape[:-1], N)
 
 
-def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO):
+def linear_packed(x, weight, bias, dequant_dtype=None, algo=_lib.ALGO_AUTO, use_spans=False):
     """y = x @ dequant(weight).T + bias through the C ABI, weight still packed.  `algo` = _lib.ALGO_* | _lib.FLAG_*.
+    use_spans: hand the re-packed span-major copy of the weight (built once, cached on the tensor) to the TMEM-fed kernel.
 
     x: CUDA fp16/bf16 [..., K]; weight: CUDA GGMLTensor (quantised type); bias: None or a CUDA tensor
     (fp32 / fp16 / bf16, rounded to x.dtype inside the kernel exactly like ops.py:205-207 does)."""
     N, K = tuple(weight.tensor_shape)
     if x.shape[-1] != K:
         raise ValueError(f"linear_packed: input features {x.shape[-1]} != weight in_features {K}")
-    return _launch_linear(x, _plain(weight), weight.tensor_type, N, K, None if bias is None else _plain(bias),
-                          math_code(dequant_dtype, x.dtype), algo)
+    wraw = _plain(weight)
+    spans = span_layout(weight, wraw) if use_spans else None
+    return _launch_linear(x, wraw, weight.tensor_type, N, K, None if bias is None else _plain(bias),
+                          math_code(dequant_dtype, x.dtype), algo, spans)
 
 
 def linear_dense(x, weight, bias=None):
@@ -357,6 +393,10 @@ class GGMLOps(comfy_ops.manual_cast):
         #            element for the hot formats, fp16 W fed to the tensor core without the cast to bf16
         #   "exact"  only routes whose weight operand is bit-identical to the reference's `dequantize_tensor(...).to(dtype)`
         linear_numerics = "fast"
+        # Weights whose canonical rows the TMA engine cannot stage (Q2_K / Q3_K / Q6_K / IQ4_XS, Q8_0 at K = 2432 ...) get a
+        # re-packed span-major shadow copy on first use (one extra copy of the packed bytes in HBM, csrc/repack.cu) so that
+        # they too run on the TMEM-fed kernel; False keeps them on the reference-exact routes.
+        repack_spans = True
 
         def _fused_ok(self, input):
             w = self.weight
@@ -403,7 +443,8 @@ class GGMLOps(comfy_ops.manual_cast):
                 w = self.weight
                 qtype, (N, K) = w.tensor_type, w.tensor_shape          # plain Python attributes: no subclass dispatch
                 wraw = w.as_subclass(torch.Tensor)
-                if wraw.device != dev:
+                resident = wraw.device == dev
+                if not resident:
                     wraw = wraw.to(dev)                                # offloaded module: packed bytes H2D
                 b = self.bias
                 if b is not None:
@@ -418,8 +459,15 @@ class GGMLOps(comfy_ops.manual_cast):
                     if input.dtype == torch.bfloat16 and K % 8 == 0 and N % 8 == 0:   # already dense: straight to the tensor-core GEMM
                         y = linear_dense(input, wraw.view(torch.bfloat16).view(N, K), b)
                 elif M <= GEMV_MAX_M or N % 8 == 0:                    # (the M <= 8 kernel stores per element: any N)
-                    algo = _lib.ALGO_AUTO if self.linear_numerics == "fast" else _lib.ALGO_AUTO | _lib.FLAG_EXACT_W
-                    y = _launch_linear(input, wraw, qtype, N, K, b, math_code(self.dequant_dtype, input.dtype), algo)
+                    math = math_code(self.dequant_dtype, input.dtype)
+                    algo, spans = _lib.ALGO_AUTO, None
+                    if self.linear_numerics != "fast":
+                        algo |= _lib.FLAG_EXACT_W
+                    elif (self.repack_spans and resident and math == _F16_CODE and N % 8 == 0 and qtype != _Q.BF16
+                          and needs_span_layout(qtype, K)):
+                        spans = span_layout(w, wraw)                   # cached on the tensor after the first forward
+                        algo = _lib.ALGO_FUSED_TMEM
+                    y = _launch_linear(input, wraw, qtype, N, K, b, math, algo, spans)
                 if y is not None:
                     return self._add_lora(y, input, terms) if terms else y
             weight, bias = self.cast_bias_weight(input)

@@ -155,6 +155,23 @@ int ggufb200_linear(int ggml_type, const void *W_packed, int64_t N, int64_t K, c
                     int64_t ldy, void *workspace, size_t workspace_bytes, int algo, void *stream);
 
 /*
+ * Span-major shadow layout ("one-time GPU repack").  The canonical GGUF rows (loader.py:96-120) can be
+ * staged by the TMA engine only when a row's 256-wide K-span and the row stride are multiples of 16 bytes; Q2_K / Q3_K /
+ * Q6_K / IQ4_XS blocks (84 / 110 / 210 / 136 bytes) and e.g. Q8_0 rows of 2432 elements (2584 bytes) are not.
+ * ggufb200_repack() writes a copy out[span][row padded to 256][pitch] (pitch = span bytes padded to a multiple of 16, zero
+ * filled) that GGUFB200_ALGO_FUSED_TMEM stages with one bulk copy per tile for EVERY block format and every K.  The
+ * canonical bytes are not modified (GGMLTensor / state_dict semantics are the reference's); the copy is a cache owned by
+ * the caller: ggufb200_repack_bytes() bytes, 16-byte aligned, valid as long as the caller keeps it.
+ * ggufb200_linear_spans() = ggufb200_linear() with that copy at hand: AUTO then takes the TMEM-fed kernel for every format
+ * (W_packed is still required: the reference-exact routes and EXACT_W read the canonical bytes).
+ */
+size_t ggufb200_repack_bytes(int ggml_type, int64_t N, int64_t K);
+int ggufb200_repack(int ggml_type, const void *W_packed, int64_t N, int64_t K, void *out, void *stream);
+int ggufb200_linear_spans(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X,
+                          int64_t M, int64_t ldx, int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y,
+                          int64_t ldy, void *workspace, size_t workspace_bytes, int algo, void *stream);
+
+/*
  * Plain tensor-core GEMM on an already-dense weight: Y = X * W^T (+bias), W[N,K] in
  * act_dtype.  Used for the F16/BF16 (torch-compatible) Linears of a model and as the
  * second half of GGUFB200_ALGO_DEQUANT_MMA.
