@@ -17,7 +17,7 @@ F16, BF16, F32 = 0, 1, 2
 ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA, ALGO_FUSED_TMEM = 0, 1, 2, 3, 4
 ALGO_MASK = 0xFF
 # per-call switches OR-ed into `algo` (include/ggufb200.h)
-FLAG_EXACT_W, FLAG_GENERIC, FLAG_TILE384, FLAG_NOSPLIT, FLAG_UNSTAGED = 0x100, 0x200, 0x400, 0x800, 0x1000
+FLAG_EXACT_W, FLAG_GENERIC, FLAG_TILE384, FLAG_NOSPLIT, FLAG_UNSTAGED, FLAG_WCAST = 0x100, 0x200, 0x400, 0x800, 0x1000, 0x2000
 OP_DEQUANT, OP_LINEAR, OP_ROWS, OP_LINEAR_MMA = 0, 1, 2, 3
 
 
@@ -68,6 +68,9 @@ def lib() -> ctypes.CDLL:
     L.ggufb200_repack_bytes.restype = c_sz
     L.ggufb200_repack_bytes.argtypes = [c_int, c_i64, c_i64]
     L.ggufb200_repack.argtypes = [c_int, c_vp, c_i64, c_i64, c_vp, c_vp]
+    if hasattr(L, "ggufb200_linear_lora"):
+        L.ggufb200_linear_lora.argtypes = [c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                           c_vp, c_sz, c_int, c_vp]
     L.ggufb200_gemm.argtypes = [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_vp, c_int, c_vp, c_i64, c_vp]
     _lib = L
     return L
@@ -82,5 +85,5 @@ EXPORTS = (
     "ggufb200_version", "ggufb200_strerror", "ggufb200_type_info", "ggufb200_supported", "ggufb200_dequant",
     "ggufb200_unpack_int", "ggufb200_dequant_rows", "ggufb200_linear_workspace", "ggufb200_linear", "ggufb200_gemm",
     "ggufb200_set_tuning", "ggufb200_linear_plan", "ggufb200_linear_workspace_ex",
-    "ggufb200_repack_bytes", "ggufb200_repack", "ggufb200_linear_spans",
+    "ggufb200_repack_bytes", "ggufb200_repack", "ggufb200_linear_spans", "ggufb200_linear_lora",
 )

@@ -24,7 +24,7 @@ int gemm3_dense_dispatch(const void *W, long long N, long long K, long long ldw,
                          int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
                          long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
-                         int flags, cudaStream_t st);
+                         int flags, const void *loraT, long long ldt, const void *loraU, cudaStream_t st);
 bool gemm4_supported(int type, const void *W, long long N, long long K);
 size_t gemm4_workspace(long long M, long long N, long long K, int flags);
 void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items);
@@ -112,6 +112,7 @@ static int g4_flags(int flags)
     int f = (flags & GGUFB200_FLAG_GENERIC) ? 0 : 1;
     if (flags & GGUFB200_FLAG_TILE384) f |= 2;
     if (flags & GGUFB200_FLAG_NOSPLIT) f |= 4;
+    if (flags & GGUFB200_FLAG_WCAST) f |= 8;
     return f;
 }
 
@@ -256,9 +257,15 @@ size_t ggufb200_linear_workspace(int ggml_type, int64_t M, int64_t N, int64_t K,
     return ggufb200_linear_workspace_ex(ggml_type, M, N, K, act_dtype, kF16, algo);
 }
 
+struct LoraSide {
+    const void *T;      // [M, 64] activation dtype: x * down^T, zero padded beyond the rank
+    int64_t ldt;
+    const void *U;      // [N, 64] fp16: scale * up, zero padded
+};
+
 static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx,
                        int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y, int64_t ldy, void *workspace,
-                       size_t workspace_bytes, int algo, void *stream)
+                       size_t workspace_bytes, int algo, void *stream, const LoraSide *lora = nullptr)
 {
     int bs, ts;
     if (!type_geom(ggml_type, &bs, &ts)) return GGUFB200_E_TYPE;
@@ -285,6 +292,11 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
     if (!aligned16(X) || (ldx % 8) != 0) return GGUFB200_E_ALIGN;
     if (vec_y && (!aligned16(Y) || (ldy % 8) != 0)) return GGUFB200_E_ALIGN;
     if (workspace && !aligned16(workspace) && r.ws) return GGUFB200_E_ALIGN;
+    if (lora) {     // the rank-r update rides as one extra k-block of the TMEM-fed kernel: no other route can carry it
+        if (r.algo != GGUFB200_ALGO_FUSED_TMEM) return GGUFB200_E_UNSUPPORTED;
+        if (!lora->T || !lora->U) return GGUFB200_E_NULL;
+        if (!aligned16(lora->T) || !aligned16(lora->U) || lora->ldt < 64 || (lora->ldt % 8) != 0) return GGUFB200_E_ALIGN;
+    }
     if (int rc = device_check()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -304,7 +316,7 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
         long long span_stride = 0;
         if (W_spans) repack_bytes(ggml_type, N, K, nullptr, &span_stride);
         return gemm4_fused_dispatch(ggml_type, W_packed, W_spans, span_stride, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, workspace,
-                                    ws_avail, g4_flags(flags), st);
+                                    ws_avail, g4_flags(flags), lora ? lora->T : nullptr, lora ? lora->ldt : 0, lora ? lora->U : nullptr, st);
     }
     case GGUFB200_ALGO_DEQUANT_MMA: {
         if (ws_avail < dense) return GGUFB200_E_WORKSPACE;
@@ -330,6 +342,15 @@ int ggufb200_linear_spans(int ggml_type, const void *W_packed, const void *W_spa
 {
     return linear_impl(ggml_type, W_packed, W_spans, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, workspace, workspace_bytes,
                        algo, stream);
+}
+
+int ggufb200_linear_lora(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M, int64_t ldx,
+                         int act_dtype, const void *bias, int bias_dtype, const void *T, int64_t ldt, const void *U, void *Y, int64_t ldy,
+                         void *workspace, size_t workspace_bytes, int algo, void *stream)
+{
+    const LoraSide side{T, ldt, U};
+    return linear_impl(ggml_type, W_packed, W_spans, N, K, X, M, ldx, act_dtype, kF16, bias, bias_dtype, Y, ldy, workspace, workspace_bytes, algo,
+                       stream, &side);
 }
 
 size_t ggufb200_repack_bytes(int ggml_type, int64_t N, int64_t K)

@@ -13,5 +13,6 @@ for f in api dequant rows gemv gemm2 gemm3 gemm4 repack; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libggufb200.so build/api.o build/dequant.o build/rows.o build/gemv.o build/gemm2.o build/gemm3.o build/gemm4.o build/repack.o
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libggufb200.so.tmp build/api.o build/dequant.o build/rows.o build/gemv.o build/gemm2.o build/gemm3.o build/gemm4.o build/repack.o
+mv -f libggufb200.so.tmp libggufb200.so     # atomic: a concurrent reader (gpurun snapshot) never sees a half-written library
 echo "built $(pwd)/libggufb200.so"

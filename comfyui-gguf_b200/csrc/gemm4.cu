@@ -71,6 +71,7 @@ struct G4Params {
     int ttiles, ftiles, splits;
     int spans_total, spans_per_split;
     int n_items;
+    const uint16_t *loraU;   // LoRA: fp16 [N, 64] = scale * up, zero padded beyond the rank (nullptr: no LoRA k-block)
 };
 
 __device__ __forceinline__ void g4_tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
@@ -94,16 +95,26 @@ __device__ __forceinline__ void g4_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         : "memory");
 }
 
-// kind::f16 instruction descriptor: D = f32, A = f16 (the dequantised weight), B = activation dtype, both K-major,
-// UMMA M = 256 (pair), N = TT
-template <int ACT, int TT> __device__ __forceinline__ constexpr uint32_t g4_idesc()
+// kind::f16 instruction descriptor: D = f32, A = the dequantised weight (f16, or bf16 when the producers cast it: WCAST),
+// B = activation dtype, both K-major, UMMA M = 256 (pair), N = TT
+template <int ACT, int TT, bool WCAST> __device__ __forceinline__ constexpr uint32_t g4_idesc()
 {
     const uint32_t bfmt = ACT == kBF16 ? 1u : 0u;
-    return (1u << 4) | (0u << 7) | (bfmt << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t afmt = (WCAST && ACT == kBF16) ? 1u : 0u;
+    return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// fp16 pair -> bf16 pair (round to nearest even), the cast the reference applies to W before F.linear (dequant.py:23)
+__device__ __forceinline__ uint32_t g4_h2_to_bf2(uint32_t h)
+{
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+    const __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+    return *reinterpret_cast<const uint32_t *>(&b);
 }
 
 struct G4Item {
     int split, ftile, ttile, span0, nspans;
+    int lora;      // this item ends with the LoRA k-block: A = U rows (scale * up), B = T = x * down^T  (K range 0 only)
 };
 __device__ __forceinline__ G4Item g4_item(const G4Params &p, int item)
 {
@@ -115,12 +126,14 @@ __device__ __forceinline__ G4Item g4_item(const G4Params &p, int item)
     it.ttile = rem - it.ftile * p.ttiles;
     it.span0 = it.split * p.spans_per_split;
     it.nspans = min(p.spans_per_split, p.spans_total - it.span0);
+    it.lora = (p.loraU != nullptr && it.split == 0) ? 1 : 0;
     return it;
 }
 
-template <class Q, int ACT, int TT, int ACCS, bool FAST>
+template <class Q, int ACT, int TT, int ACCS, bool FAST, bool WCAST>
 __global__ void __launch_bounds__(kG4Threads, 1)
-gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const G4Params p)
+gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT,
+             const G4Params p)
 {
     constexpr int SPAN = SpanOf<Q>::BYTES;        // packed bytes of one row's K-span (coordinate step of the 2-D tensor map)
     constexpr int PITCH = SpanOf<Q>::PITCH;       // row pitch of a staged span (== SPAN whenever the 2-D tensor map is legal)
@@ -186,15 +199,17 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int item = pair; item < p.n_items; item += n_pairs) {
                 const G4Item w = g4_item(p, item);
                 const int m0 = w.ttile * (TT * ACCS) + (int)rank * (TT / 2);
-                const int kb0 = w.span0 * 4, nkb = w.nspans * 4;
+                const int kb0 = w.span0 * 4, nkb = w.nspans * 4 + w.lora;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % XS;
                     mbar_wait(&empty_x[s], (uint32_t)(((it / XS) & 1) ^ 1));
                     uint8_t *dst = xt + s * Cfg::XSTAGE;
                     const uint32_t bar = mapa_u32(smem_u32(&full_x[s]), 0);
                     if (leader) mbar_arrive_expect_tx(&full_x[s], 2 * Cfg::XSTAGE);
+                    const bool lora_kb = kb == w.nspans * 4;      // the extra k-block reads T = x * down^T instead of X
 #pragma unroll
-                    for (int a = 0; a < ACCS; ++a) tma_load_2d_pair(dst + a * Cfg::X_BYTES, &tmX, bar, (kb0 + kb) * kG2BK, m0 + a * TT);
+                    for (int a = 0; a < ACCS; ++a)
+                        tma_load_2d_pair(dst + a * Cfg::X_BYTES, lora_kb ? &tmT : &tmX, bar, lora_kb ? 0 : (kb0 + kb) * kG2BK, m0 + a * TT);
                 }
             }
         }
@@ -226,11 +241,11 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA, one thread)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = g4_idesc<ACT, TT>();
+            constexpr uint32_t idesc = g4_idesc<ACT, TT, WCAST>();
             int it = 0, ti = 0;
             for (int item = pair; item < p.n_items; item += n_pairs, ++ti) {
                 const G4Item w = g4_item(p, item);
-                const int nkb = w.nspans * 4;
+                const int nkb = w.nspans * 4 + w.lora;
                 // accumulator slot(s) of this item must have been drained by the epilogue
                 if constexpr (ACCS == 1) {
                     mbar_wait_cluster(&tmem_empty[ti & 1], (uint32_t)(((ti >> 1) & 1) ^ 1));
@@ -272,7 +287,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             int it = 0;
             for (int item = pair; item < p.n_items; item += n_pairs) {
                 const G4Item w = g4_item(p, item);
-                const int nkb = w.nspans * 4;
+                const int nkb = w.nspans * 4 + w.lora;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int sa = it % AST;
                     mbar_wait(&full_a[sa], (uint32_t)((it / AST) & 1));
@@ -288,19 +303,29 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const int quad = warp & 3;                           // TMEM lane quadrant of this warp
         const int row = quad * 32 + lane;                    // feature row inside this CTA's 128
         const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TM::A_BASE;
-        int sp = 0, itg = 0;                                 // spans seen; k-blocks this group has produced
+        int sp = 0, it0 = 0;                                 // spans seen; global k-block index at the start of the item
+        auto store_half = [&](uint32_t taddr, int half, const uint32_t (&o)[16]) {
+            if constexpr (WCAST && ACT == kBF16) {
+                uint32_t c[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) c[j] = g4_h2_to_bf2(o[j]);
+                g4_tmem_st16(taddr + (uint32_t)(half * 16), c);
+            } else {
+                g4_tmem_st16(taddr + (uint32_t)(half * 16), o);
+            }
+        };
         for (int item = pair; item < p.n_items; item += n_pairs) {
             const G4Item w = g4_item(p, item);
-            for (int i = 0; i < w.nspans; ++i, ++sp, ++itg) {
+            for (int i = 0; i < w.nspans; ++i, ++sp) {
                 const int b = sp % NP;
-                const int it = 4 * itg + g;                  // global k-block index of this group's quarter of the span
+                const int it = it0 + 4 * i + g;              // global k-block index of this group's quarter of the span
                 const int sa = it % AST;
                 mbar_wait(&full_p[b], (uint32_t)((sp / NP) & 1));
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / AST) & 1) ^ 1));
                 g2_fence_after();
                 const uint8_t *src = packed + b * Cfg::P_BYTES + row * PITCH;
                 const uint32_t taddr = lane_base + (uint32_t)(sa * 32);
-                Prod::run64(src, g, [&](int half, const uint32_t (&o)[16]) { g4_tmem_st16(taddr + (uint32_t)(half * 16), o); });
+                Prod::run64(src, g, [&](int half, const uint32_t (&o)[16]) { store_half(taddr, half, o); });
                 g4_tmem_st_wait();
                 g2_fence_before();
                 __syncwarp();
@@ -309,6 +334,32 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_arrive(&empty_p[b]);
                 }
             }
+            if (w.lora && g == 0) {
+                // LoRA k-block: this row of U = scale * up (64 fp16, zero padded beyond the rank) straight from global memory
+                const int it = it0 + 4 * w.nspans;
+                const int sa = it % AST;
+                mbar_wait(&empty_a[sa], (uint32_t)(((it / AST) & 1) ^ 1));
+                g2_fence_after();
+                const long long n = (long long)w.ftile * 256 + rank * 128 + row;
+                const uint32_t taddr = lane_base + (uint32_t)(sa * 32);
+                const uint4 *urow = reinterpret_cast<const uint4 *>(p.loraU + (n < p.N ? n : 0) * 64);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t o[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (n < p.N) v = urow[half * 4 + q4];
+                        o[4 * q4] = v.x; o[4 * q4 + 1] = v.y; o[4 * q4 + 2] = v.z; o[4 * q4 + 3] = v.w;
+                    }
+                    store_half(taddr, half, o);
+                }
+                g4_tmem_st_wait();
+                g2_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[sa]);
+            }
+            it0 += 4 * w.nspans + w.lora;
         }
     } else if (warp >= kG4EpiWarp0) {
         // ===================== epilogue: D[feature (lane), token (column)] -> Y[token, feature]
@@ -457,22 +508,27 @@ struct G4Args {
     long long ldy;
     void *ws;
     size_t ws_bytes;
-    int fast, want_accs, nosplit;
+    int fast, want_accs, nosplit, wcast;
+    const void *loraT;         // LoRA: T = x * down^T, [M, 64] activation dtype, row stride ldt (nullptr: none)
+    long long ldt;
+    const void *loraU;         // LoRA: U = scale * up, fp16 [N, 64] contiguous
     cudaStream_t st;
 };
 
-template <class Q, int ACT, int TT, int ACCS, bool FAST>
+template <class Q, int ACT, int TT, int ACCS, bool FAST, bool WCAST>
 static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
 {
     constexpr int SPAN = SpanOf<Q>::BYTES;
     using Cfg = G4Cfg<SpanOf<Q>::PITCH, TT, ACCS>;
-    auto kern = gemm4_kernel<Q, ACT, TT, ACCS, FAST>;
+    auto kern = gemm4_kernel<Q, ACT, TT, ACCS, FAST, WCAST>;
     static unsigned char attr[64] = {};
     if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
     G2EncodeFn fn = g2_encode_fn();
     if (!fn) return GGUFB200_E_CUDA;
-    CUtensorMap tmX, tmW;
+    CUtensorMap tmX, tmW, tmT;
     if (!g2_make_map(&tmX, a.X, a.M, a.K, a.ldx, ACT, TT / 2)) return GGUFB200_E_CUDA;
+    tmT = tmX;
+    if (a.loraT && !g2_make_map(&tmT, a.loraT, a.M, 64, a.ldt, ACT, TT / 2)) return GGUFB200_E_CUDA;
     const long long row_bytes = a.K / Q::BS * Q::TS;
     if (a.Wspan) {
         tmW = tmX;   // unused by the kernel in this mode
@@ -500,6 +556,7 @@ static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
     p.spans_total = (int)((a.K + 255) / 256);
     p.spans_per_split = pl.spans_per_split;
     p.n_items = pl.n_items;
+    p.loraU = a.loraT ? reinterpret_cast<const uint16_t *>(a.loraU) : nullptr;
     int pairs = sm_count() / 2;
     if (pairs > p.n_items) pairs = p.n_items;
     cudaLaunchConfig_t cfg{};
@@ -514,15 +571,23 @@ static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+    return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmT, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <class Q, int ACT, bool FAST, bool WCAST> static int g4_tiles2(const G4Args &a, const G4Plan &pl, float *partial)
+{
+    if (pl.tt == 32) return g4_launch<Q, ACT, 32, 1, FAST, WCAST>(a, pl, partial);
+    if (pl.tt == 128) return g4_launch<Q, ACT, 128, 1, FAST, WCAST>(a, pl, partial);
+    if (pl.accs == 2) return g4_launch<Q, ACT, 192, 2, FAST, WCAST>(a, pl, partial);
+    return g4_launch<Q, ACT, 192, 1, FAST, WCAST>(a, pl, partial);
 }
 
 template <class Q, int ACT, bool FAST> static int g4_tiles(const G4Args &a, const G4Plan &pl, float *partial)
 {
-    if (pl.tt == 32) return g4_launch<Q, ACT, 32, 1, FAST>(a, pl, partial);
-    if (pl.tt == 128) return g4_launch<Q, ACT, 128, 1, FAST>(a, pl, partial);
-    if (pl.accs == 2) return g4_launch<Q, ACT, 192, 2, FAST>(a, pl, partial);
-    return g4_launch<Q, ACT, 192, 1, FAST>(a, pl, partial);
+    if constexpr (ACT == kBF16) {
+        if (a.wcast) return g4_tiles2<Q, ACT, FAST, true>(a, pl, partial);
+    }
+    return g4_tiles2<Q, ACT, FAST, false>(a, pl, partial);
 }
 
 template <class Q, int ACT> static int g4_run(const G4Args &a)
@@ -550,13 +615,15 @@ template <class Q> static bool g4_canonical_ok(const void *W, long long K)
     return SpanOf<Q>::BYTES % 16 == 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
 }
 
-// flags: bit 0 = fast producers (single-FMA float step), bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K
+// flags: bit 0 = fast producers (single-FMA float step), bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K,
+// bit 3 = producers cast W to the activation dtype (bf16 A operand instead of the mixed f16 x bf16 UMMA)
 int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
                          long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
-                         int flags, cudaStream_t st)
+                         int flags, const void *loraT, long long ldt, const void *loraU, cudaStream_t st)
 {
     if (N % 8 != 0 || K % 8 != 0) return GGUFB200_E_UNSUPPORTED;
-    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags & 1, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0, st};
+    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags & 1, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0,
+             (flags & 8) ? 1 : 0, loraT, ldt, loraU, st};
 #define GGUFB200_G4_CASE(T)                                                                    \
     case T:                                                                                    \
         if (!Wspan && !g4_canonical_ok<Block<T>>(W, K)) return GGUFB200_E_UNSUPPORTED;         \

@@ -32,6 +32,29 @@ template <class Q> struct SpanOf {
     static constexpr int PITCH = BYTES % 16 == 0 ? BYTES : ((PAD16 / 16) % 2 == 1 ? PAD16 : PAD16 + 16);
 };
 
+// 16-byte / 4-byte loads of a staged span.  On the device the span always lives in shared memory (gemm4.cu): say so, or
+// the compiler emits generic loads (LD.E.128 + address-space resolution) instead of LDS.128.
+GG_HD uint4 ld_span16(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    return v;
+#else
+    return *reinterpret_cast<const uint4 *>(p);
+#endif
+}
+GG_HD uint32_t ld_span4(const uint8_t *p)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)));
+    return v;
+#else
+    return *reinterpret_cast<const uint32_t *>(p);
+#endif
+}
+
 GG_HD uint32_t h2_bits(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
 GG_HD __half2 bits_h2(uint32_t v) { return *reinterpret_cast<__half2 *>(&v); }
 
@@ -114,9 +137,9 @@ template <> struct FastProducer<Block<T_Q4_K>> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *blk, int kq, Emit &&emit)
     {
-        const uint4 h = *reinterpret_cast<const uint4 *>(blk);                       // d | dmin << 16, scales[12]
-        const uint4 qa = *reinterpret_cast<const uint4 *>(blk + 16 + 32 * kq);       // bytes 0..15 of the 64-element group
-        const uint4 qb = *reinterpret_cast<const uint4 *>(blk + 32 + 32 * kq);       // bytes 16..31
+        const uint4 h = ld_span16(blk);                       // d | dmin << 16, scales[12]
+        const uint4 qa = ld_span16(blk + 16 + 32 * kq);       // bytes 0..15 of the 64-element group
+        const uint4 qb = ld_span16(blk + 32 + 32 * kq);       // bytes 16..31
         uint32_t sc, mn;
         k_scale_pair(h.y, h.z, h.w, kq, sc, mn);
         const __half2 dm0 = k_dm(h.x, sc, mn), dm1 = k_dm(h.x, sc >> 8, mn >> 8);
@@ -153,10 +176,10 @@ template <> struct FastProducer<Block<T_Q5_K>> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *blk, int kq, Emit &&emit)
     {
-        const uint4 h = *reinterpret_cast<const uint4 *>(blk);
-        const uint4 ha = *reinterpret_cast<const uint4 *>(blk + 16), hb = *reinterpret_cast<const uint4 *>(blk + 32);   // qh[32]
-        const uint4 qa = *reinterpret_cast<const uint4 *>(blk + 48 + 32 * kq);
-        const uint4 qb = *reinterpret_cast<const uint4 *>(blk + 64 + 32 * kq);
+        const uint4 h = ld_span16(blk);
+        const uint4 ha = ld_span16(blk + 16), hb = ld_span16(blk + 32);   // qh[32]
+        const uint4 qa = ld_span16(blk + 48 + 32 * kq);
+        const uint4 qb = ld_span16(blk + 64 + 32 * kq);
         uint32_t sc, mn;
         k_scale_pair(h.y, h.z, h.w, kq, sc, mn);
         const __half2 dm0 = k_dm(h.x, sc, mn), dm1 = k_dm(h.x, sc >> 8, mn >> 8);
@@ -194,13 +217,13 @@ template <> struct FastProducer<Block<T_Q8_0>> {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             // blocks 2kq (offset 68kq, 4-byte aligned) and 2kq+1 (offset 68kq + 34 = 2 mod 4)
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(span + 68 * kq + (half ? 32 : 0));
+            const uint8_t *p = span + 68 * kq + (half ? 32 : 0);
             uint32_t o[16];
             if (half == 0) {
                 // word 0 = d | x0 x1 << 16; words 1..7 = x2..x29; word 8 low half = x30 x31
                 uint32_t wd[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) wd[i] = p[i];
+                for (int i = 0; i < 9; ++i) wd[i] = ld_span4(p + 4 * i);
                 const __half2 D = __half2half2(__ushort_as_half((unsigned short)(wd[0] & 0xFFFFu)));
 #pragma unroll
                 for (int i = 0; i < 9; ++i) wd[i] ^= 0x80808080u;
@@ -215,7 +238,7 @@ template <> struct FastProducer<Block<T_Q8_0>> {
                 // p = block start - 2: word 0 high half = d; words 1..8 = x0..x31
                 uint32_t wd[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) wd[i] = p[i];
+                for (int i = 0; i < 9; ++i) wd[i] = ld_span4(p + 4 * i);
                 const __half2 D = __half2half2(__ushort_as_half((unsigned short)(wd[0] >> 16)));
 #pragma unroll
                 for (int i = 1; i < 9; ++i) wd[i] ^= 0x80808080u;
@@ -239,10 +262,9 @@ template <> struct FastProducer<Block<T_Q4_0>> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *span, int kq, Emit &&emit)
     {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(span + 36 * kq);
         uint32_t wd[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) wd[i] = p[i];
+        for (int i = 0; i < 9; ++i) wd[i] = ld_span4(span + 36 * kq + 4 * i);
         const __half2 k1032 = __half2half2(__ushort_as_half((unsigned short)(0x6400u + 8u)));
         const __half2 k72 = __half2half2(__ushort_as_half((unsigned short)0x5480u));      // 64 + 8
 #pragma unroll
@@ -279,16 +301,15 @@ template <> struct FastProducer<Block<T_Q6_K>> {
         const int hh = kq >> 1, up = kq & 1;
         // ql bytes 64h + (r & 63), nibble r >> 6 -> for this quarter: all 64 bytes ql[64h .. 64h+63], nibble `up`
         // qh bytes 128 + 32h + (r & 31), 2-bit field r >> 5 -> fields 2*up (first 32 elements) and 2*up + 1 (last 32)
-        const uint4 *ql = reinterpret_cast<const uint4 *>(blk + 64 * hh);
-        const uint4 *qh = reinterpret_cast<const uint4 *>(blk + 128 + 32 * hh);
-        const uint4 h0 = qh[0], h1 = qh[1];
+        const uint8_t *ql = blk + 64 * hh;
+        const uint4 h0 = ld_span16(blk + 128 + 32 * hh), h1 = ld_span16(blk + 144 + 32 * hh);
         const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const uint32_t sw = *reinterpret_cast<const uint32_t *>(blk + 192 + 4 * kq);     // four int8 scales of this quarter
-        const __half d = __ushort_as_half(*reinterpret_cast<const uint16_t *>(blk + 208));
+        const uint32_t sw = ld_span4(blk + 192 + 4 * kq);     // four int8 scales of this quarter
+        const __half d = __ushort_as_half((unsigned short)(ld_span4(blk + 208) & 0xFFFFu));    // bytes 210, 211 are row padding of the span layout
         const __half2 k1056 = __half2half2(__ushort_as_half((unsigned short)(0x6400u + 32u)));
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const uint4 l0 = ql[2 * half], l1 = ql[2 * half + 1];
+            const uint4 l0 = ld_span16(ql + 32 * half), l1 = ld_span16(ql + 32 * half + 16);
             const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
             // scales: elements 0..15 of this 32-run use scale 2*half, 16..31 use 2*half+1
             const int s0 = (int)(int8_t)(sw >> (16 * half)), s1 = (int)(int8_t)(sw >> (16 * half + 8));

@@ -143,7 +143,10 @@ def span_layout(weight, wraw):
     return out
 
 
-def _launch_linear(x, wraw, qtype, N, K, bias, math, algo, spans=None):
+LORA_MAX_RANK = 64     # the LoRA k-block of the TMEM-fed kernel is one 64-wide k-block
+
+
+def _launch_linear(x, wraw, qtype, N, K, bias, math, algo, spans=None, lora=None):
     """The call itself.  x: CUDA fp16/bf16 [..., K]; wraw: PLAIN uint8 tensor holding the packed rows on x.device;
     bias: PLAIN tensor on x.device or None.  Kept free of tensor-subclass traffic (every attribute read on a GGMLTensor
     goes through __torch_function__) and of per-call object construction: for short activations the host side of this
@@ -173,7 +176,14 @@ def _launch_linear(x, wraw, qtype, N, K, bias, math, algo, spans=None):
         ws = torch.empty(need, dtype=torch.uint8, device=device)
         ws_ptr = ws.data_ptr()
     index = device.index
-    if spans is not None:
+    if lora is not None:
+        t_pad, u_pad = lora           # T = x * down^T [M, 64] act dtype, U = scale * up [N, 64] fp16 (zero padded)
+
+        def call():
+            return L.ggufb200_linear_lora(qcode, w_ptr, None if spans is None else spans.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act,
+                                          bias_ptr, bias_code, t_pad.data_ptr(), t_pad.stride(0), u_pad.data_ptr(), y.data_ptr(), N, ws_ptr, need,
+                                          algo, _current_stream_ptr(index))
+    elif spans is not None:
         def call():
             return L.ggufb200_linear_spans(qcode, w_ptr, spans.data_ptr(), N, K, x2.data_ptr(), M, x2.stride(0), act, math, bias_ptr, bias_code,
                                            y.data_ptr(), N, ws_ptr, need, algo, _current_stream_ptr(index))
@@ -422,6 +432,28 @@ class GGMLOps(comfy_ops.manual_cast):
                 return None
             return terms
 
+        # LoRA inside the fused kernel (csrc/gemm4.cu: one extra k-block): U = scale * up (fp16 [N, 64]) and
+        # down (act dtype [64, K]), zero padded to rank 64 and cached per patch set; per forward only T = x * down^T
+        # ([M, 64], this package's dense tcgen05 GEMM) is computed before the fused call.
+        lora_in_kernel = True
+
+        def _lora_operands(self, terms, dev, dtype):
+            key = tuple((id(up), id(down), float(scale)) for scale, up, down in terms) + (str(dev), dtype)
+            cached = self.__dict__.get("_gg_lora")
+            if cached is not None and cached[0] == key:
+                return cached[1], cached[2]
+            N, K = tuple(self.weight.tensor_shape)
+            down_pad = torch.zeros(LORA_MAX_RANK, K, device=dev, dtype=dtype)
+            u_pad = torch.zeros(N, LORA_MAX_RANK, device=dev, dtype=torch.float16)
+            r0 = 0
+            for scale, up, down in terms:
+                r = down.shape[0]
+                down_pad[r0:r0 + r] = down.to(device=dev, dtype=dtype)
+                u_pad[:, r0:r0 + r] = (up.to(device=dev, dtype=torch.float32) * scale).to(torch.float16)
+                r0 += r
+            self.__dict__["_gg_lora"] = (key, down_pad, u_pad)
+            return down_pad, u_pad
+
         def _add_lora(self, y, input, terms):
             x2 = input.reshape(-1, input.shape[-1])
             y2 = y.view(-1, y.shape[-1])
@@ -467,7 +499,16 @@ class GGMLOps(comfy_ops.manual_cast):
                           and needs_span_layout(qtype, K)):
                         spans = span_layout(w, wraw)                   # cached on the tensor after the first forward
                         algo = _lib.ALGO_FUSED_TMEM
-                    y = _launch_linear(input, wraw, qtype, N, K, b, math, algo, spans)
+                    lora = None
+                    if (terms and self.lora_in_kernel and self.linear_numerics == "fast" and math == _F16_CODE and N % 8 == 0
+                            and qtype != _Q.BF16 and sum(d.shape[0] for _s, _u, d in terms) <= LORA_MAX_RANK
+                            and (spans is not None or not needs_span_layout(qtype, K))):
+                        down_pad, u_pad = self._lora_operands(terms, dev, input.dtype)
+                        lora = (linear_dense(input.reshape(-1, K), down_pad), u_pad)       # T = x * down^T, [M, 64]
+                        algo = _lib.ALGO_FUSED_TMEM
+                    y = _launch_linear(input, wraw, qtype, N, K, b, math, algo, spans, lora)
+                    if lora is not None:
+                        return y
                 if y is not None:
                     return self._add_lora(y, input, terms) if terms else y
             weight, bias = self.cast_bias_weight(input)

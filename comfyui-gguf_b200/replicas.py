@@ -67,6 +67,42 @@ def aggregate_throughput(units_per_rank: float, local_ms: float) -> tuple[float,
     return total_units / (t_ms * 1e-3), t_ms
 
 
+def parse_cpulist(text: str) -> list[int]:
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (format of /sys/devices/system/node/node*/cpulist)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this replica's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned staging
+    buffers (first touch then places them on that node).  With N replicas sharing two sockets, the end-to-end path (pinned
+    host -> H2D -> kernel -> D2H) otherwise crosses the socket interconnect for half of the ranks.  Best effort: returns what
+    was done; never raises."""
+    info = {"bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:      # no sysfs, no permission, old torch: stay unbound
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 def shutdown():
     if dist.is_initialized():
         dist.destroy_process_group()

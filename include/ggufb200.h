@@ -82,6 +82,7 @@ extern "C" {
 #define GGUFB200_FLAG_TILE384 0x400
 #define GGUFB200_FLAG_NOSPLIT 0x800
 #define GGUFB200_FLAG_UNSTAGED 0x1000
+#define GGUFB200_FLAG_WCAST 0x2000 /* FUSED_TMEM, bf16 activations: producers cast W to bf16 (A = bf16) instead of feeding fp16 W */
 
 int ggufb200_version(void);
 const char *ggufb200_strerror(int rc);
@@ -170,6 +171,20 @@ int ggufb200_repack(int ggml_type, const void *W_packed, int64_t N, int64_t K, v
 int ggufb200_linear_spans(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X,
                           int64_t M, int64_t ldx, int act_dtype, int math_dtype, const void *bias, int bias_dtype, void *Y,
                           int64_t ldy, void *workspace, size_t workspace_bytes, int algo, void *stream);
+
+/*
+ * Packed-weight Linear with a low-rank (LoRA) update folded into the SAME kernel (replaces the
+ * per-forward dequant + comfy.lora.calculate_weight + F.linear of ops.py:171-190 / nodes.py:43-47 for plain LoRA patches):
+ *     Y = X * dequant(W)^T + T * U^T (+ bias),   T = X * down^T  [M, 64] act_dtype (row stride ldt, zero padded beyond the
+ *     total rank R <= 64),   U = scale * up  [N, 64] fp16, contiguous, zero padded.
+ * The update is one extra 64-wide k-block of GGUFB200_ALGO_FUSED_TMEM (U rows go to tensor memory like a dequantised
+ * span, the T tile is TMA-fed like an activation tile): no second pass over Y, no extra GEMM launch for the up-projection.
+ * algo must resolve to GGUFB200_ALGO_FUSED_TMEM (AUTO without EXACT_W on a weight that route supports, or explicit),
+ * otherwise GGUFB200_E_UNSUPPORTED.  W_spans may be NULL.  fp16 dequant math.
+ */
+int ggufb200_linear_lora(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M,
+                         int64_t ldx, int act_dtype, const void *bias, int bias_dtype, const void *T, int64_t ldt, const void *U,
+                         void *Y, int64_t ldy, void *workspace, size_t workspace_bytes, int algo, void *stream);
 
 /*
  * Plain tensor-core GEMM on an already-dense weight: Y = X * W^T (+bias), W[N,K] in

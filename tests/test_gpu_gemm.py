@@ -231,3 +231,71 @@ def test_auto_route_large_m_through_layer(pkg):
     assert rel_fro(y.float().cpu().numpy(), ref) <= TOL_TMEM[torch.bfloat16]
     lin.linear_numerics = "exact"
     assert rel_fro(lin(x).float().cpu().numpy(), ref) <= TOL
+
+
+# ---------------------------------------------------------------- span-major shadow layout (csrc/repack.cu)
+def _pitch(qt):
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    span = 256 // bs * ts
+    if span % 16 == 0:
+        return span, span
+    pad = (span + 15) // 16 * 16
+    return span, pad if (pad // 16) % 2 == 1 else pad + 16
+
+
+@pytest.mark.parametrize("qt", BLOCK_TYPES, ids=lambda q: q.name)
+@pytest.mark.parametrize("N,K", [(300, 768), (264, 1280), (130, 320)])
+def test_repack_layout_is_a_pure_byte_permutation(pkg, qt, N, K):
+    """out[span][row padded to 256][pitch]: the canonical bytes of (row, span), zero padding everywhere else -- bit-exact."""
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    if K % bs:
+        pytest.skip("K must be a multiple of the block size")
+    raw, w = _weight(pkg, qt, N, K, seed=int(qt) + N)
+    got = pkg.ops.span_layout(w, pkg.ops._plain(w)).cpu().numpy()
+    span, pitch = _pitch(qt)
+    spans, n_pad, row_bytes = -(-K // 256), -(-N // 256) * 256, K // bs * ts
+    want = np.zeros((spans, n_pad, pitch), dtype=np.uint8)
+    for s in range(spans):
+        chunk = raw[:, s * span:min((s + 1) * span, row_bytes)]
+        want[s, :N, :chunk.shape[1]] = chunk
+    assert got.size == want.size == pkg.lib.lib().ggufb200_repack_bytes(int(qt), N, K)
+    assert np.array_equal(got.reshape(want.shape), want)
+    assert pkg.ops.span_layout(w, pkg.ops._plain(w)).data_ptr() == pkg.ops.span_layout(w, pkg.ops._plain(w)).data_ptr()   # cached
+
+
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("qt", BLOCK_TYPES, ids=lambda q: q.name)
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_tmem_fused_from_span_layout_all_types(pkg, qt, dt, generic):
+    """Every block format -- including the ones no tensor map can stage (Q2_K / Q3_K / Q6_K / IQ4_XS) -- on the TMEM-fed kernel."""
+    M, N, K = 300, 264, 1024
+    _raw, w = _weight(pkg, qt, N, K, seed=int(qt) + 5)
+    x = torch.randn(M, K, device=DEV, dtype=dt)
+    b = torch.randn(N, device=DEV) * 0.1
+    algo = pkg.lib.ALGO_FUSED_TMEM | (pkg.lib.FLAG_GENERIC if generic else 0)
+    y = pkg.ops.linear_packed(x, w, b, None, algo, use_spans=True)
+    W = pkg.dequant.dequantize_tensor(w, dt)
+    ref = _ref(x, W, b)
+    assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= TOL_TMEM[dt]
+    ideal = _ideal(pkg, x, w, b)
+    assert (y.double() - ideal).norm().item() <= 1.02 * (ref.double() - ideal).norm().item()
+    if qt in TMEM_TYPES:
+        assert torch.equal(y, pkg.ops.linear_packed(x, w, b, None, algo)), "span-major and canonical staging must agree bit for bit"
+
+
+@pytest.mark.parametrize("M", [2, 700])
+def test_sd35_shape_q8_0_rows_run_on_the_tmem_kernel_through_the_layer(pkg, M):
+    """SD3.5-large hidden size 2432: 2584-byte Q8_0 rows.  The layer builds the span-major copy on first use and the TMEM-fed
+    kernel serves it (K = 2432 is not a multiple of 256: the last span is half empty)."""
+    N, K = 7296, 2432
+    _raw, w = _weight(pkg, Q.Q8_0, N, K, seed=2)
+    lin = pkg.ops.GGMLOps.Linear(K, N)
+    lin.load_state_dict({"weight": w})
+    x = torch.randn(M, K, device=DEV, dtype=torch.float16)
+    y = lin(x)
+    assert "_gg_spans" in lin.weight.__dict__, "the fast contract should have re-packed this weight"
+    W = pkg.dequant.dequantize_tensor(w, torch.float16)
+    assert rel_fro(y.float().cpu().numpy(), _ref(x, W, None).float().cpu().numpy()) <= TOL
+    lin.repack_spans = False
+    y2 = lin(x)
+    assert rel_fro(y2.float().cpu().numpy(), _ref(x, W, None).float().cpu().numpy()) <= TOL

@@ -117,8 +117,51 @@ def run_sd35(steps=6, ref_steps=2, depth=38, img_tokens=4096, txt_tokens=333):
             "ms_per_step": ms, "reference_chain_ms": ms_ref, "speedup_vs_reference_chain": ms_ref / ms, "output_rel_err_vs_reference_chain": rel}
 
 
+def parity(which, numerics):
+    """Per-Linear parity (tools/flux_harness.py::LinearParity) of a full-size model under one numerics contract."""
+    ops_mod, dq = ge._sub("ops"), ge._sub("dequant")
+    ops_mod.GGMLOps.Linear.linear_numerics = numerics
+    dev = torch.device("cuda:0")
+    with torch.no_grad():
+        if which == "flux":
+            model = fh.FluxShapeDiT(ops_mod.GGMLOps)
+            fh.load_shared(model, fh.build_state_dict(model, ops_mod.GGMLTensor, dev)).to(dev)
+            inp = fh.make_inputs(dev, torch.bfloat16)
+            call = lambda: model(**inp)
+        elif which == "sd35":
+            kw = dict(hidden=2432, heads=38, depth=38, depth_single=0, ctx=4096, vec=2048)
+            model = fh.FluxShapeDiT(ops_mod.GGMLOps, **kw)
+            fh.load_shared(model, fh.build_state_dict(model, ops_mod.GGMLTensor, dev, block_qtype=fh.Q.Q8_0)).to(dev)
+            inp = fh.make_inputs(dev, torch.bfloat16, img_tokens=4096, txt_tokens=333)
+            inp["y"] = torch.randn(1, 2048, device=dev).to(torch.bfloat16)
+            call = lambda: model(**inp)
+        else:
+            model = T5ShapeEncoder(ops_mod.GGMLOps, 24)
+            sd = build_sd(model, ops_mod.GGMLTensor, dev, fh.Q.Q5_K, bias=False, scale=5e-5)
+            gen = torch.Generator(device=dev).manual_seed(5)
+            table = ops_mod.GGMLTensor(fh.random_packed(fh.Q.Q5_K, 32128, 4096, dev, gen, scale=1e-3), tensor_type=fh.Q.Q5_K, tensor_shape=torch.Size((32128, 4096)))
+            model.shared.weight = nn.Parameter(table, requires_grad=False)
+            attach(model, sd).to(dev)
+            ids = torch.randint(0, 32128, (1, 512), device=dev)
+            call = lambda: model(ids)
+        with fh.LinearParity(model, dq) as lp:
+            call()
+        out = lp.summary()
+    out.update(model=which, numerics=numerics, activation="bf16",
+               budget="1e-3 (exact: weight operand bit-identical to the reference's)" if numerics == "exact" else
+                      "8e-3 (fast, bf16 = 1e-3 in fp16 ulps; the TMEM route keeps W in fp16)")
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["t5", "sd35"]
+    if which[0] == "parity":
+        for m in (which[1:] or ["flux", "sd35", "t5"]):
+            for numerics in ("exact", "fast"):
+                print(json.dumps(parity(m, numerics)), flush=True)
+        sys.exit(0)
     if "t5" in which:
         print(json.dumps(run_t5()), flush=True)
     if "sd35" in which:

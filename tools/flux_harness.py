@@ -250,3 +250,61 @@ def linear_flops(model, img_tokens, txt_tokens, batch=1):
             M = 1
         total += 2 * batch * M * mod.in_features * mod.out_features
     return total
+
+
+# ------------------------------------------------------------------ per-Linear parity at model scale
+class LinearParity:
+    """Forward hooks on every quantised Linear of `model`: the layer's output (whatever route AUTO picked for it) against the
+    reference arithmetic ON THE SAME INPUT -- fp32-accumulated x @ W^T + bias with W = the bit-exact standalone dequant
+    (dequant.py float sequence) rounded to the activation dtype, bias rounded to the activation dtype (ops.py:193-211,
+    242-244), result rounded to the activation dtype.  Isolates the per-layer error from the drift a deep network
+    accumulates: `records` = (name, qtype, M, N, K, relative Frobenius error)."""
+
+    def __init__(self, model, dequant_mod, every=1):
+        self.model, self.dq, self.every = model, dequant_mod, every
+        self.records, self.handles = [], []
+
+    def __enter__(self):
+        idx = 0
+        for name, mod in self.model.named_modules():
+            w = getattr(mod, "weight", None)
+            if not hasattr(mod, "in_features") or w is None or getattr(w, "tensor_type", None) is None:
+                continue
+            idx += 1
+            if idx % self.every:
+                continue
+            self.handles.append(mod.register_forward_hook(self._hook(name)))
+        return self
+
+    def _hook(self, name):
+        def fn(mod, args, out):
+            x = args[0]
+            if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+                return
+            w = mod.weight
+            K = x.shape[-1]
+            x2 = x.reshape(-1, K)
+            W = self.dq.dequantize_tensor(w, x.dtype, getattr(mod, "dequant_dtype", None)).as_subclass(torch.Tensor)
+            ref = x2.float() @ W.float().t()
+            b = getattr(mod, "bias", None)
+            if b is not None:
+                ref = ref + b.as_subclass(torch.Tensor).to(x.device).to(x.dtype).float()
+            ref = ref.to(x.dtype).float()
+            y = out.reshape(-1, out.shape[-1]).float()
+            rel = float(((y - ref).norm() / ref.norm().clamp_min(1e-30)).item())
+            self.records.append((name, w.tensor_type.name, x2.shape[0], W.shape[0], K, rel))
+            del W, ref
+        return fn
+
+    def __exit__(self, *exc):
+        for h in self.handles:
+            h.remove()
+
+    def summary(self):
+        import collections
+        by = collections.defaultdict(list)
+        for _n, qt, M, _N, _K, rel in self.records:
+            by[(qt, "M<=8" if M <= 8 else ("M<=1024" if M <= 1024 else "M>1024"))].append(rel)
+        rows = {f"{qt} {cls}": {"layers": len(v), "max": max(v), "median": sorted(v)[len(v) // 2]} for (qt, cls), v in sorted(by.items())}
+        worst = max(self.records, key=lambda r: r[-1]) if self.records else None
+        return {"per_class": rows, "worst": worst, "layers": len(self.records)}
