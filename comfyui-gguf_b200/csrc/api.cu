@@ -110,9 +110,9 @@ struct Route {
 static int g4_flags(int flags)
 {
     int f = (flags & GGUFB200_FLAG_GENERIC) ? 0 : 1;
+    if (flags & GGUFB200_FLAG_EXACT_W) f |= 16;       // hand-written producers that keep the reference's rounding sequence
     if (flags & GGUFB200_FLAG_TILE384) f |= 2;
     if (flags & GGUFB200_FLAG_NOSPLIT) f |= 4;
-    if (flags & GGUFB200_FLAG_WCAST) f |= 8;
     return f;
 }
 

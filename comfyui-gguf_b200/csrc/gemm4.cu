@@ -7,8 +7,8 @@
 // warps write their fp16 results with tcgen05.st straight into TMEM columns and W never touches shared memory: the
 // shared-memory port, which bounds both the smem-fed fused kernel (gemm2.cu: A by TMA + B by STS + UMMA reads of both
 // = 119 B/clk of 128) and the dense kernel, only carries the activation tiles (TMA write + UMMA read, <= 64 B/clk) and the
-// packed bytes (0.56 B/element).  kind::f16 takes A = f16 with B = bf16, so bf16 activations need no fp16 -> bf16
-// conversion of W either.
+// packed bytes (0.56 B/element).  (kind::f16 does NOT take A = f16 with B = bf16 -- measured: illegal-instruction trap -- so
+// with bf16 activations the producers append the reference's cast of W to bf16.)
 //
 // Cluster = 2 CTAs, tcgen05.mma.cta_group::2: UMMA M = 256 features (128 TMEM lanes per CTA), N = TT tokens.
 //   TMEM (512 columns per CTA):  [0, 2*TT) two accumulator slots of TT fp32 columns,  [A_BASE, A_BASE + 32*AST) ring of
@@ -95,8 +95,8 @@ __device__ __forceinline__ void g4_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         : "memory");
 }
 
-// kind::f16 instruction descriptor: D = f32, A = the dequantised weight (f16, or bf16 when the producers cast it: WCAST),
-// B = activation dtype, both K-major, UMMA M = 256 (pair), N = TT
+// kind::f16 instruction descriptor: D = f32, A (the dequantised weight) and B (the activations) in the activation dtype,
+// both K-major, UMMA M = 256 (pair), N = TT
 template <int ACT, int TT, bool WCAST> __device__ __forceinline__ constexpr uint32_t g4_idesc()
 {
     const uint32_t bfmt = ACT == kBF16 ? 1u : 0u;
@@ -130,16 +130,21 @@ __device__ __forceinline__ G4Item g4_item(const G4Params &p, int item)
     return it;
 }
 
-template <class Q, int ACT, int TT, int ACCS, bool FAST, bool WCAST>
+template <class Q, int ACT, int TT, int ACCS, int PROD>
 __global__ void __launch_bounds__(kG4Threads, 1)
 gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT,
              const G4Params p)
 {
+    // kind::f16 rejects A = f16 with B = bf16 (illegal-instruction trap on B200: profiles/r02_probe_mixed_operand_types.txt),
+    // so with bf16 activations the producers cast W to bf16 -- the cast the reference applies before F.linear (dequant.py:23)
+    constexpr bool WCAST = ACT == kBF16;
     constexpr int SPAN = SpanOf<Q>::BYTES;        // packed bytes of one row's K-span (coordinate step of the 2-D tensor map)
     constexpr int PITCH = SpanOf<Q>::PITCH;       // row pitch of a staged span (== SPAN whenever the 2-D tensor map is legal)
     using Cfg = G4Cfg<PITCH, TT, ACCS>;
     using TM = G4Tmem<TT>;
-    using Prod = typename std::conditional<FAST, FastProducer<Q>, Producer<Q>>::type;
+    // PROD: 0 = generic producers (reference sequence, every format), 1 = hand-written, fused multiply-add step,
+    //       2 = hand-written, reference sequence (bit-identical weight)
+    using Prod = typename std::conditional<PROD == 0, Producer<Q>, FastProducer<Q, PROD == 1>>::type;
     constexpr int XS = Cfg::XS, NP = Cfg::NP, AST = TM::AST;
 
     extern __shared__ uint8_t g4_smem_raw[];
@@ -191,6 +196,10 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     cluster_sync_all();
     g2_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster hand-shake) overlaps the tail of
+    // the previous kernel in the stream; nothing below may touch global memory before that kernel's writes are visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer: activation tiles
@@ -508,19 +517,19 @@ struct G4Args {
     long long ldy;
     void *ws;
     size_t ws_bytes;
-    int fast, want_accs, nosplit, wcast;
+    int fast, want_accs, nosplit;
     const void *loraT;         // LoRA: T = x * down^T, [M, 64] activation dtype, row stride ldt (nullptr: none)
     long long ldt;
     const void *loraU;         // LoRA: U = scale * up, fp16 [N, 64] contiguous
     cudaStream_t st;
 };
 
-template <class Q, int ACT, int TT, int ACCS, bool FAST, bool WCAST>
+template <class Q, int ACT, int TT, int ACCS, int PROD>
 static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
 {
     constexpr int SPAN = SpanOf<Q>::BYTES;
     using Cfg = G4Cfg<SpanOf<Q>::PITCH, TT, ACCS>;
-    auto kern = gemm4_kernel<Q, ACT, TT, ACCS, FAST, WCAST>;
+    auto kern = gemm4_kernel<Q, ACT, TT, ACCS, PROD>;
     static unsigned char attr[64] = {};
     if (!ensure_dynamic_smem(kern, Cfg::SMEM, attr)) return GGUFB200_E_CUDA;
     G2EncodeFn fn = g2_encode_fn();
@@ -564,31 +573,30 @@ static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
     cfg.blockDim = dim3(kG4Threads);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = a.st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // the kernel executes griddepcontrol.wait before its first global access
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmT, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 
-template <class Q, int ACT, bool FAST, bool WCAST> static int g4_tiles2(const G4Args &a, const G4Plan &pl, float *partial)
+template <class Q, int ACT, int PROD> static int g4_tiles(const G4Args &a, const G4Plan &pl, float *partial)
 {
-    if (pl.tt == 32) return g4_launch<Q, ACT, 32, 1, FAST, WCAST>(a, pl, partial);
-    if (pl.tt == 128) return g4_launch<Q, ACT, 128, 1, FAST, WCAST>(a, pl, partial);
-    if (pl.accs == 2) return g4_launch<Q, ACT, 192, 2, FAST, WCAST>(a, pl, partial);
-    return g4_launch<Q, ACT, 192, 1, FAST, WCAST>(a, pl, partial);
+    if (pl.tt == 32) return g4_launch<Q, ACT, 32, 1, PROD>(a, pl, partial);
+    if (pl.tt == 128) return g4_launch<Q, ACT, 128, 1, PROD>(a, pl, partial);
+    if (pl.accs == 2) return g4_launch<Q, ACT, 192, 2, PROD>(a, pl, partial);
+    return g4_launch<Q, ACT, 192, 1, PROD>(a, pl, partial);
 }
 
-template <class Q, int ACT, bool FAST> static int g4_tiles(const G4Args &a, const G4Plan &pl, float *partial)
-{
-    if constexpr (ACT == kBF16) {
-        if (a.wcast) return g4_tiles2<Q, ACT, FAST, true>(a, pl, partial);
-    }
-    return g4_tiles2<Q, ACT, FAST, false>(a, pl, partial);
-}
+// does the fused-multiply-add flag change the hand-written producer of this format?  (only Q4_K / Q5_K have a two-rounding step)
+template <class Q> struct FmaMatters {
+    static constexpr bool value = Q::TS == 144 || Q::TS == 176;
+};
 
 template <class Q, int ACT> static int g4_run(const G4Args &a)
 {
@@ -597,9 +605,16 @@ template <class Q, int ACT> static int g4_run(const G4Args &a)
     if (wsb > kG4SplitWsCap) wsb = kG4SplitWsCap;
     const G4Plan pl = g4_plan(a.M, a.N, a.K, wsb, a.want_accs, !a.nosplit);
     float *partial = pl.splits > 1 ? reinterpret_cast<float *>(a.ws) : nullptr;
+    // a.fast: 0 = generic producers, 1 = hand-written + fused multiply-add, 2 = hand-written + reference sequence
     int rc;
-    if (a.fast && FastProducer<Q>::fast) rc = g4_tiles<Q, ACT, true>(a, pl, partial);
-    else rc = g4_tiles<Q, ACT, false>(a, pl, partial);
+    if (a.fast == 0 || !FastProducer<Q>::fast) {
+        rc = g4_tiles<Q, ACT, 0>(a, pl, partial);
+    } else if (a.fast == 2) {
+        if constexpr (FmaMatters<Q>::value) rc = g4_tiles<Q, ACT, 2>(a, pl, partial);
+        else rc = g4_tiles<Q, ACT, 1>(a, pl, partial);
+    } else {
+        rc = g4_tiles<Q, ACT, 1>(a, pl, partial);
+    }
     if (rc != GGUFB200_OK || !partial) return rc;
     const long long work = a.M * (a.N / 8);
     const unsigned grid = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
@@ -615,15 +630,15 @@ template <class Q> static bool g4_canonical_ok(const void *W, long long K)
     return SpanOf<Q>::BYTES % 16 == 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
 }
 
-// flags: bit 0 = fast producers (single-FMA float step), bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K,
-// bit 3 = producers cast W to the activation dtype (bf16 A operand instead of the mixed f16 x bf16 UMMA)
+// flags: bits 0 / 4 = producers (1: hand-written, fused multiply-add; 17: hand-written, reference sequence; 0: generic),
+// bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K
 int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
                          long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
                          int flags, const void *loraT, long long ldt, const void *loraU, cudaStream_t st)
 {
     if (N % 8 != 0 || K % 8 != 0) return GGUFB200_E_UNSUPPORTED;
-    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, flags & 1, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0,
-             (flags & 8) ? 1 : 0, loraT, ldt, loraU, st};
+    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, (flags & 1) ? ((flags & 16) ? 2 : 1) : 0, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0,
+             loraT, ldt, loraU, st};
 #define GGUFB200_G4_CASE(T)                                                                    \
     case T:                                                                                    \
         if (!Wspan && !g4_canonical_ok<Block<T>>(W, K)) return GGUFB200_E_UNSUPPORTED;         \

@@ -85,7 +85,12 @@ template <class Q> struct Producer {
     }
 };
 
-template <class Q> struct FastProducer : Producer<Q> {};   // formats without a hand-written producer use the generic one
+// FMA = true: the per-element step of Q4_K / Q5_K is one fused multiply-add (the `fast` contract); false: multiply, round,
+// subtract, round -- the reference's sequence, bit-identical weight (the other hand-written producers have a single-rounding
+// float step in the reference already and ignore the flag).
+template <class Q, bool FMA = true> struct FastProducer : Producer<Q> {};   // formats without a hand-written producer use the generic one
+
+
 
 GG_HD __half2 h2_fma(__half2 a, __half2 b, __half2 c)
 {
@@ -97,6 +102,12 @@ GG_HD __half2 h2_fma(__half2 a, __half2 b, __half2 c)
     const double x = (double)fa.x * (double)fb.x + (double)fc.x, y = (double)fa.y * (double)fb.y + (double)fc.y;
     return __halves2half2(__double2half(x), __double2half(y));
 #endif
+}
+
+template <bool FMA> GG_HD __half2 k_step(__half2 q, __half2 D, __half2 nM)
+{
+    if constexpr (FMA) return h2_fma(q, D, nM);
+    else return __hadd2_rn(__hmul2_rn(D, q), nM);        // fp16(fp16(D*q) - M): x + (-M) == x - M exactly
 }
 
 // (sc, mn) bytes -> (d*sc, dmin*mn) as one rounded half2 product, exactly the reference's fp16(d*sc), fp16(dmin*mn)
@@ -133,7 +144,7 @@ template <bool HIGH> GG_HD void bytes_to_h2(uint32_t v, __half2 &lo, __half2 &hi
 }
 
 // ------------------------------------------------------------------ Q4_K  (dequant.py:180-195)
-template <> struct FastProducer<Block<T_Q4_K>> {
+template <bool FMA> struct FastProducer<Block<T_Q4_K>, FMA> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *blk, int kq, Emit &&emit)
     {
@@ -151,8 +162,8 @@ template <> struct FastProducer<Block<T_Q4_K>> {
             for (int i = 0; i < 8; ++i) {
                 __half2 a, b;
                 bytes_to_h2<false>(w[i] & 0x0F0F0F0Fu, a, b);
-                o[2 * i] = h2_bits(h2_fma(a, D, nM));
-                o[2 * i + 1] = h2_bits(h2_fma(b, D, nM));
+                o[2 * i] = h2_bits(k_step<FMA>(a, D, nM));
+                o[2 * i + 1] = h2_bits(k_step<FMA>(b, D, nM));
             }
             emit(0, o);
         }
@@ -163,8 +174,8 @@ template <> struct FastProducer<Block<T_Q4_K>> {
             for (int i = 0; i < 8; ++i) {
                 __half2 a, b;
                 bytes_to_h2<true>(w[i] & 0xF0F0F0F0u, a, b);
-                o[2 * i] = h2_bits(h2_fma(a, D, nM));
-                o[2 * i + 1] = h2_bits(h2_fma(b, D, nM));
+                o[2 * i] = h2_bits(k_step<FMA>(a, D, nM));
+                o[2 * i + 1] = h2_bits(k_step<FMA>(b, D, nM));
             }
             emit(1, o);
         }
@@ -172,7 +183,7 @@ template <> struct FastProducer<Block<T_Q4_K>> {
 };
 
 // ------------------------------------------------------------------ Q5_K  (dequant.py:159-178)
-template <> struct FastProducer<Block<T_Q5_K>> {
+template <bool FMA> struct FastProducer<Block<T_Q5_K>, FMA> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *blk, int kq, Emit &&emit)
     {
@@ -197,8 +208,8 @@ template <> struct FastProducer<Block<T_Q5_K>> {
                 const uint32_t u = lo | (((qh[i] >> sb) & 0x01010101u) << 4);      // 5-bit value per byte
                 __half2 a, b;
                 bytes_to_h2<false>(u, a, b);
-                o[2 * i] = h2_bits(h2_fma(a, D, nM));
-                o[2 * i + 1] = h2_bits(h2_fma(b, D, nM));
+                o[2 * i] = h2_bits(k_step<FMA>(a, D, nM));
+                o[2 * i + 1] = h2_bits(k_step<FMA>(b, D, nM));
             }
             emit(half, o);
         }
@@ -209,7 +220,7 @@ template <> struct FastProducer<Block<T_Q5_K>> {
 // eight 34-byte blocks per span; block b starts at 34*b (4-byte aligned for even b, 2 mod 4 for odd b).  d*x has a single
 // rounding in the reference as well, so this producer is bit-exact; it only replaces the 2-byte loads of the generic one
 // by aligned 4-byte words.
-template <> struct FastProducer<Block<T_Q8_0>> {
+template <bool FMA> struct FastProducer<Block<T_Q8_0>, FMA> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *span, int kq, Emit &&emit)
     {
@@ -258,7 +269,7 @@ template <> struct FastProducer<Block<T_Q8_0>> {
 // ------------------------------------------------------------------ Q4_0  (dequant.py:115-123)
 // eight 18-byte blocks per span; d*(q-8) has a single rounding in the reference: bit-exact, aligned word loads.
 // A 64-wide quarter = blocks 2kq, 2kq+1 = 36 bytes at offset 36kq (4-byte aligned): [d0 qs0[16]] [d1 qs1[16]].
-template <> struct FastProducer<Block<T_Q4_0>> {
+template <bool FMA> struct FastProducer<Block<T_Q4_0>, FMA> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *span, int kq, Emit &&emit)
     {
@@ -293,7 +304,7 @@ template <> struct FastProducer<Block<T_Q4_0>> {
 // [ql 128][qh 64][scales i8 16][d]; 210-byte blocks are only 2-byte aligned in the canonical layout, so this producer is
 // used with the re-packed (16-byte aligned, padded) span layout only.  (d*sc) and (*q) round separately in the reference;
 // here q*(d*sc) is one rounded product of the reference's fp16(d*sc) -- the same single multiply, hence bit-exact.
-template <> struct FastProducer<Block<T_Q6_K>> {
+template <bool FMA> struct FastProducer<Block<T_Q6_K>, FMA> {
     static constexpr bool fast = true;
     template <class Emit> static GG_HD void run64(const uint8_t *blk, int kq, Emit &&emit)
     {

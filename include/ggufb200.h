@@ -68,12 +68,13 @@ extern "C" {
 /* Per-call switches (no process-wide state):
  *   EXACT_W    AUTO only picks routes whose weight operand is bit-identical to what the reference hands to F.linear
  *              (dequant.py float sequence with per-op rounding, then the cast to the activation dtype).  Without it AUTO
- *              prefers GGUFB200_ALGO_FUSED_TMEM, whose contract is: integer unpack bit-exact; sub-block scale products
- *              as the reference; the per-element float step is ONE fused multiply-add in fp16 (hot formats) and the fp16
- *              weight is fed to the tensor core unrounded (no cast of W to bf16) -- the result is at least as close to
- *              the exact product as the reference's and within 1e-3 (fp16) / 8e-3 (bf16, = the same bound in bf16 ulps)
- *              of it.
- *   GENERIC    FUSED_TMEM: use the reference-rounding producers instead of the hand-written ones
+ *              prefers GGUFB200_ALGO_FUSED_TMEM with its hand-written producers, whose contract is: integer unpack
+ *              bit-exact; sub-block scale products as the reference; for Q4_K / Q5_K the per-element float step is ONE
+ *              fused multiply-add in fp16 (the correctly rounded value of the step) instead of multiply + subtract; then
+ *              the reference's cast to the activation dtype.  The result is as close to the exact product as the
+ *              reference's and within 1e-3 (fp16) / 8e-3 (bf16, = the same bound in bf16 ulps) of it.
+ *   GENERIC    FUSED_TMEM: producers that follow the reference's rounding sequence op for op -> the weight operand is
+ *              bit-identical to the reference's in fp16 AND bf16 (EXACT_W-compatible)
  *   TILE384    FUSED_TMEM: 384-token items (both accumulator slots per dequantised tile, epilogue not overlapped)
  *   NOSPLIT    FUSED_MMA / FUSED_TMEM: never cut K into ranges
  *   UNSTAGED   FUSED_MMA: producers read packed rows from global memory instead of TMA-staged shared memory */
@@ -82,7 +83,6 @@ extern "C" {
 #define GGUFB200_FLAG_TILE384 0x400
 #define GGUFB200_FLAG_NOSPLIT 0x800
 #define GGUFB200_FLAG_UNSTAGED 0x1000
-#define GGUFB200_FLAG_WCAST 0x2000 /* FUSED_TMEM, bf16 activations: producers cast W to bf16 (A = bf16) instead of feeding fp16 W */
 
 int ggufb200_version(void);
 const char *ggufb200_strerror(int rc);

@@ -71,9 +71,9 @@ template <class Q, int ACT> int run_fast16(const uint8_t *blocks, long long n_bl
 
 // W producers of the TMEM-fed fused kernel (produce.cuh): spans of `span_bytes` per row, 16-byte aligned, rows of
 // 256 elements; out: fp16 bit patterns, n_spans * 256 elements
-template <class Q, bool FAST> int run_produce(const uint8_t *spans, long long n_spans, int pitch, uint16_t *out)
+template <class Q, int PROD> int run_produce(const uint8_t *spans, long long n_spans, int pitch, uint16_t *out)
 {
-    using P = typename std::conditional<FAST, FastProducer<Q>, Producer<Q>>::type;
+    using P = typename std::conditional<PROD == 0, Producer<Q>, FastProducer<Q, PROD == 1>>::type;
     for (long long s = 0; s < n_spans; ++s)
         for (int kq = 0; kq < 4; ++kq)
             P::run64(spans + s * pitch, kq, [&](int half, const uint32_t (&o)[16]) {
@@ -111,13 +111,15 @@ int hostf_fast16(int type, const uint8_t *blocks, long long n_blocks, uint32_t *
     return -1;
 }
 
-// produce.cuh: fast != 0 selects FastProducer<Q> (falls back to the generic one for formats without a hand-written producer).
-// Returns 1 when the fast request was served by a hand-written producer, 0 when by the generic one.
+// produce.cuh: fast = 0 generic Producer<Q>; 1 hand-written with the fused multiply-add step; 2 hand-written with the reference
+// sequence (falls back to the generic one for formats without a hand-written producer).
+// Returns 1 when the request was served by a hand-written producer, 0 when by the generic one.
 int hostf_produce(int type, const uint8_t *spans, long long n_spans, int pitch, uint16_t *out, int fast)
 {
     switch (type) {
-#define X(T) case T: if (fast) { run_produce<Block<T>, true>(spans, n_spans, pitch, out); return FastProducer<Block<T>>::fast ? 1 : 0; } \
-                     run_produce<Block<T>, false>(spans, n_spans, pitch, out); return 0;
+#define X(T) case T: if (fast == 1) { run_produce<Block<T>, 1>(spans, n_spans, pitch, out); return FastProducer<Block<T>>::fast ? 1 : 0; } \
+                     if (fast == 2) { run_produce<Block<T>, 2>(spans, n_spans, pitch, out); return FastProducer<Block<T>>::fast ? 1 : 0; } \
+                     run_produce<Block<T>, 0>(spans, n_spans, pitch, out); return 0;
         HOSTF_TYPES(X)
 #undef X
     }

@@ -123,3 +123,33 @@ def test_workspace_contract_follows_the_route(pkg):
     buf = (ctypes.c_uint8 * 4096)()
     p16 = (ctypes.addressof(buf) + 15) & ~15
     assert L.ggufb200_dequant_rows(int(Q.Q4_K), p16, 4, 100, p16, 1, p16, 0, 0, None) == -4
+
+
+def test_span_layout_geometry_without_gpu(pkg):
+    """ggufb200_repack_bytes = spans * rows padded to 256 * pitch; pitch = span bytes, padded to an odd multiple of 16 when the
+    span is not a multiple of 16 bytes (csrc/produce.cuh SpanOf::PITCH)."""
+    L = pkg.lib.lib()
+    want_pitch = {Q.Q4_0: 144, Q.Q4_1: 160, Q.Q5_0: 176, Q.Q5_1: 192, Q.Q8_0: 272, Q.Q2_K: 112, Q.Q3_K: 112, Q.Q4_K: 144, Q.Q5_K: 176,
+                  Q.Q6_K: 240, Q.IQ4_NL: 144, Q.IQ4_XS: 144}
+    for qt, pitch in want_pitch.items():
+        bs, ts = gguf.GGML_QUANT_SIZES[qt]
+        span = 256 // bs * ts
+        assert pitch % 16 == 0 and pitch >= span and (pitch == span or (pitch // 16) % 2 == 1)
+        assert L.ggufb200_repack_bytes(int(qt), 300, 768) == 3 * 512 * pitch
+        assert L.ggufb200_repack_bytes(int(qt), 256, 256) == 256 * pitch
+    assert L.ggufb200_repack_bytes(int(Q.Q8_0), 7296, 2432) == 10 * 7424 * 272      # SD3.5 shape: ragged last span
+    assert L.ggufb200_repack_bytes(int(Q.BF16), 8, 8) == 0 and L.ggufb200_repack_bytes(999, 8, 256) == 0
+    assert L.ggufb200_repack_bytes(int(Q.Q4_K), 8, 100) == 0                          # K not a multiple of the block size
+    buf = (ctypes.c_uint8 * 4096)()
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    assert L.ggufb200_repack(int(Q.BF16), p16, 8, 8, p16, None) == -1
+    assert L.ggufb200_repack(int(Q.Q4_K), None, 8, 256, p16, None) == -5
+    assert L.ggufb200_repack(int(Q.Q4_K), p16, 8, 256, p16 + 4, None) == -3
+    # the LoRA entry point validates like ggufb200_linear and needs the TMEM route
+    x = p16
+    assert L.ggufb200_linear_lora(int(Q.Q4_K), p16, None, 8, 256, x, 4, 256, 1, None, 0, x, 64, x, x, 8, None, 0,
+                                  pkg.lib.ALGO_GEMV, None) == -8
+    assert L.ggufb200_linear_lora(int(Q.Q4_K), p16, None, 8, 256, x, 4, 256, 1, None, 0, None, 64, x, x, 8, None, 0,
+                                  pkg.lib.ALGO_FUSED_TMEM, None) == -5
+    assert L.ggufb200_linear_lora(int(Q.Q4_K), p16, None, 8, 256, x, 4, 256, 1, None, 0, x, 48, x, x, 8, None, 0,
+                                  pkg.lib.ALGO_FUSED_TMEM, None) == -3

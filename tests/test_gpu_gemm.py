@@ -7,12 +7,14 @@ Reference: fp32-accumulated x @ W^T (+bias) rounded to the activation dtype, whe
 Tolerances, relative Frobenius:
   * routes whose weight operand is bit-identical to the reference's (GEMV, FUSED_MMA, DEQUANT_MMA): 1e-3 in every dtype
     (north_star's figure; only the fp32 summation order differs).
-  * FUSED_TMEM keeps W in fp16 (one fused multiply-add per element for the hot formats, no cast of W to bf16):
+  * FUSED_TMEM with FLAG_GENERIC (functor producers) or FLAG_EXACT_W (hand-written producers, reference sequence): the weight
+    operand is bit-identical as well (fp16 chain, then the cast to bf16 for bf16 activations) -> 3e-4 asserted.
+  * FUSED_TMEM default ("fast": Q4_K / Q5_K use ONE fused multiply-add per element instead of multiply + subtract):
       fp16 activations:  1e-3 against the reference arithmetic (measured ~4e-4);
       bf16 activations:  8e-3 = the same bound expressed in bf16 ulps (2^3 coarser than fp16), because ANY weight that is not
-                         bit-identical to bf16(W_ref) moves a bf16 Linear by ~2e-3 -- including the exact weight.  What is
-                         asserted in addition: the result is at least as close to the fp64 product of the exact weight as the
-                         reference's own result is."""
+                         bit-identical to bf16(W_ref) moves a bf16 Linear by ~2e-3 (measured 1.9e-3) -- even the exactly
+                         dequantised weight would.  What is asserted in addition: the result is as close to the fp64 product
+                         of the exact weight as the reference's own result is (within 5 %)."""
 import numpy as np
 import pytest
 import torch
@@ -155,34 +157,38 @@ def test_fused_gemm_flux_shapes_q4k(pkg, M, N, K):
     W32 = pkg.dequant.dequantize_tensor(w, torch.float32, torch.float32)
     ideal = (x.float() @ W32.t()).double()                  # exact weight, fp32 accumulate: ~1e-6 from the fp64 product
     del W32
-    for algo in (pkg.lib.ALGO_FUSED_TMEM, pkg.lib.ALGO_FUSED_TMEM | pkg.lib.FLAG_TILE384, pkg.lib.ALGO_FUSED_TMEM | pkg.lib.FLAG_GENERIC):
+    for algo in (pkg.lib.ALGO_FUSED_TMEM, pkg.lib.ALGO_FUSED_TMEM | pkg.lib.FLAG_TILE384, pkg.lib.ALGO_FUSED_TMEM | pkg.lib.FLAG_GENERIC,
+                 pkg.lib.ALGO_FUSED_TMEM | pkg.lib.FLAG_EXACT_W):
         y = pkg.ops.linear_packed(x, w, None, None, algo)
-        assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= TOL_TMEM[torch.bfloat16]
+        exact = bool(algo & (pkg.lib.FLAG_GENERIC | pkg.lib.FLAG_EXACT_W))
+        assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= (3e-4 if exact else TOL_TMEM[torch.bfloat16])
         err_ours = (y.double() - ideal).norm().item()
         err_ref = (ref.double() - ideal).norm().item()
-        assert err_ours <= 1.02 * err_ref, (algo, err_ours, err_ref)
+        assert err_ours <= 1.05 * err_ref, (algo, err_ours, err_ref)
 
 
 # ---------------------------------------------------------------- TMEM-fed fused kernel (csrc/gemm4.cu)
-@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+PRODUCERS = {"fast": 0, "generic": 0x200, "exact": 0x100}      # default / GGUFB200_FLAG_GENERIC / GGUFB200_FLAG_EXACT_W
+
+
+@pytest.mark.parametrize("producers", list(PRODUCERS))
 @pytest.mark.parametrize("qt", TMEM_TYPES, ids=lambda q: q.name)
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
-def test_tmem_fused_all_types(pkg, qt, dt, generic):
-    """Every format whose canonical rows can be staged by a 2-D tensor map, both producer families, ragged M and N."""
+def test_tmem_fused_all_types(pkg, qt, dt, producers):
+    """Every format whose canonical rows can be staged by a 2-D tensor map, all three producer families, ragged M and N."""
     M, N, K = 300, 264, 1024
     _raw, w = _weight(pkg, qt, N, K, seed=int(qt) + 3)
     x = torch.randn(M, K, device=DEV, dtype=dt)
     b = torch.randn(N, device=DEV) * 0.1
-    algo = pkg.lib.ALGO_FUSED_TMEM | (pkg.lib.FLAG_GENERIC if generic else 0)
-    y = pkg.ops.linear_packed(x, w, b, None, algo)
+    y = pkg.ops.linear_packed(x, w, b, None, pkg.lib.ALGO_FUSED_TMEM | PRODUCERS[producers])
     W = pkg.dequant.dequantize_tensor(w, dt)
     ref = _ref(x, W, b)
     assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= TOL_TMEM[dt]
     ideal = _ideal(pkg, x, w, b)
-    assert (y.double() - ideal).norm().item() <= 1.02 * (ref.double() - ideal).norm().item()
-    if generic and dt == torch.float16:
-        # fp16 activations + reference-rounding producers: the weight operand IS the reference's -> only summation order differs
-        assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= 2e-4
+    assert (y.double() - ideal).norm().item() <= 1.05 * (ref.double() - ideal).norm().item()
+    if producers != "fast" or qt not in (Q.Q4_K, Q.Q5_K):
+        # reference rounding sequence: the weight operand IS the reference's (in fp16 and in bf16) -> only summation order differs
+        assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= 3e-4
 
 
 @pytest.mark.parametrize("M,N,K", [(1, 512, 1024), (3, 200, 768), (8, 1032, 4096), (24, 512, 256), (33, 264, 512), (128, 256, 256),
@@ -263,22 +269,24 @@ def test_repack_layout_is_a_pure_byte_permutation(pkg, qt, N, K):
     assert pkg.ops.span_layout(w, pkg.ops._plain(w)).data_ptr() == pkg.ops.span_layout(w, pkg.ops._plain(w)).data_ptr()   # cached
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("producers", list(PRODUCERS))
 @pytest.mark.parametrize("qt", BLOCK_TYPES, ids=lambda q: q.name)
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
-def test_tmem_fused_from_span_layout_all_types(pkg, qt, dt, generic):
+def test_tmem_fused_from_span_layout_all_types(pkg, qt, dt, producers):
     """Every block format -- including the ones no tensor map can stage (Q2_K / Q3_K / Q6_K / IQ4_XS) -- on the TMEM-fed kernel."""
     M, N, K = 300, 264, 1024
     _raw, w = _weight(pkg, qt, N, K, seed=int(qt) + 5)
     x = torch.randn(M, K, device=DEV, dtype=dt)
     b = torch.randn(N, device=DEV) * 0.1
-    algo = pkg.lib.ALGO_FUSED_TMEM | (pkg.lib.FLAG_GENERIC if generic else 0)
+    algo = pkg.lib.ALGO_FUSED_TMEM | PRODUCERS[producers]
     y = pkg.ops.linear_packed(x, w, b, None, algo, use_spans=True)
     W = pkg.dequant.dequantize_tensor(w, dt)
     ref = _ref(x, W, b)
     assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= TOL_TMEM[dt]
     ideal = _ideal(pkg, x, w, b)
-    assert (y.double() - ideal).norm().item() <= 1.02 * (ref.double() - ideal).norm().item()
+    assert (y.double() - ideal).norm().item() <= 1.05 * (ref.double() - ideal).norm().item()
+    if producers != "fast" or qt not in (Q.Q4_K, Q.Q5_K):
+        assert rel_fro(y.float().cpu().numpy(), ref.float().cpu().numpy()) <= 3e-4
     if qt in TMEM_TYPES:
         assert torch.equal(y, pkg.ops.linear_packed(x, w, b, None, algo)), "span-major and canonical staging must agree bit for bit"
 

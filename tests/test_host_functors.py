@@ -250,6 +250,20 @@ def test_fast_producers(hostf, qt):
     assert np.all(np.abs(g - w) <= bound)
 
 
+@pytest.mark.parametrize("qt", sorted(EXACT_FAST | FMA_FAST, key=int), ids=lambda q: q.name)
+@pytest.mark.parametrize("wild", [False, True], ids=["trained-like", "raw-bytes"])
+def test_hand_written_producers_with_the_reference_sequence_are_bit_exact(hostf, qt, wild):
+    """FastProducer<Q, FMA = false> (GGUFB200_FLAG_EXACT_W on the TMEM route): the weight is the reference's, bit for bit."""
+    n = 1500
+    bs, ts = oracle.type_info(int(qt))
+    span = 256 // bs * ts
+    buf, raw, pitch = _spans(qt, n, seed=int(qt) + 21, wild=wild, pitch=(span + 15) // 16 * 16)
+    got = np.empty(n * 256, dtype=np.uint16)
+    assert hostf.hostf_produce(int(qt), buf.ctypes.data, n, pitch, got.ctypes.data, 2) == 1
+    want = oracle.dequant(raw.reshape(-1, ts), int(qt), oracle.DT_F16, oracle.DT_F16)
+    assert _equal_mod_nan(got, want, oracle.DT_F16)
+
+
 def test_fast_request_falls_back_to_generic_for_other_formats(hostf):
     buf, raw, pitch = _spans(Q.Q3_K, 8, seed=1, pitch=112)
     got = np.empty(8 * 256, dtype=np.uint16)

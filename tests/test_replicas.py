@@ -47,3 +47,12 @@ def test_two_replicas_gloo():
         assert abs(rate - 200.0 / 15e-3) < 1e-6   # units of BOTH replicas over the slowest time
         assert mx == 1.0
         assert seeds[0] != seeds[1]
+
+
+def test_parse_cpulist_and_numa_binding_is_best_effort(pkg):
+    import __graft_entry__ as ge
+    rep = ge._sub("replicas")
+    assert rep.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert rep.parse_cpulist("") == []
+    info = rep.bind_to_gpu_numa(0)          # no GPU here: must not raise, must report that nothing was bound
+    assert info["bound"] is False

@@ -23,7 +23,7 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_generic", lib.ALGO_FUSED_TMEM | lib.FLAG_GENERIC), ("gemv_exact", lib.ALGO_GEMV))
+ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
 side = torch.cuda.Stream()
 for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
     qt = gguf.GGMLQuantizationType[qname]

@@ -4,6 +4,8 @@ set +e
 mkdir -p gpurun_out
 P="timeout -k 10 120 python tools/probe_tmem.py"
 {
+echo "== hardware feature probe (tools/probe_ts.cu): 0 st/ld, 1 TS f16xf16, 2 TS f16 x bf16 (mixed), 3 TS bf16xbf16, 4 SS f16"
+for v in 0 4 1 3 2; do timeout -k 5 60 tools/probe_ts $v 2>&1 | tail -1; done
 echo "== A f16 M=300 (tt=192)"; $P f16 0 2>&1 | tail -2
 echo "== B f16 M=100 (tt=128)"; $P f16 0 100 264 1024 2>&1 | tail -2
 echo "== C f16 M=8 (tt=32, split-K)"; $P f16 0 8 512 2048 2>&1 | tail -2
