@@ -24,7 +24,7 @@
 //   2      TMEM allocation; relay: forwards "this CTA's A stage is complete" to the leader with one cluster-scope arrive
 //   3      TMA producer, packed weight: this CTA's 128 rows of one 256-wide K-span per copy (2-D tensor map over the raw
 //          bytes, or one bulk copy from the re-packed span-major layout), ring of NP buffers
-//   4-7    epilogue: TMEM -> registers -> (+bias, cast) -> global, one warp per TMEM lane quadrant
+//   4-7    epilogue: TMEM -> registers -> (+bias, cast) -> [32 tokens][128 features] smem tile -> one bulk tensor store per tile
 //   8-23   dequant producers: group g = (warp-8)/4 owns the k-blocks with kb % 4 == g, warp quadrant = warp % 4, lane = feature
 //          row; a thread unpacks 64 consecutive k of its row (produce.cuh) and stores them with two tcgen05.st.32x32b.x16
 // K is processed in whole 256-wide spans: a ragged tail (K % 256 != 0) is zero-filled by the TMA engine on both operands.
@@ -51,10 +51,11 @@ template <int SPAN_BYTES, int TT, int ACCS> struct G4Cfg {
     static constexpr int XSTAGE = ACCS * X_BYTES;
     static constexpr int XS = TT >= 128 ? (ACCS == 2 ? 4 : 6) : 8;
     static constexpr int P_BYTES = (128 * SPAN_BYTES + 1023) & ~1023;
-    static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - XS * XSTAGE;
+    static constexpr int EPI_BYTES = 2 * 32 * 128 * 2;             // two [32 tokens][128 features] 16-bit output tiles (TMA-stored)
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 1024 - EPI_BYTES - XS * XSTAGE;
     static constexpr int NP_MAX = TT >= 128 ? 4 : 8;
     static constexpr int NP = BUDGET / P_BYTES < NP_MAX ? BUDGET / P_BYTES : NP_MAX;
-    static constexpr int SMEM = XS * XSTAGE + NP * P_BYTES + 1024 + 1024;
+    static constexpr int SMEM = XS * XSTAGE + NP * P_BYTES + EPI_BYTES + 1024 + 1024;
     static_assert(NP >= 2, "packed span buffers do not fit");
     static_assert(X_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 };
@@ -133,7 +134,7 @@ __device__ __forceinline__ G4Item g4_item(const G4Params &p, int item)
 template <class Q, int ACT, int TT, int ACCS, int PROD>
 __global__ void __launch_bounds__(kG4Threads, 1)
 gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT,
-             const G4Params p)
+             const __grid_constant__ CUtensorMap tmY, const G4Params p)
 {
     // kind::f16 rejects A = f16 with B = bf16 (illegal-instruction trap on B200: profiles/r02_probe_mixed_operand_types.txt),
     // so with bf16 activations the producers cast W to bf16 -- the cast the reference applies before F.linear (dequant.py:23)
@@ -150,7 +151,8 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     extern __shared__ uint8_t g4_smem_raw[];
     uint8_t *xt = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(g4_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *packed = xt + XS * Cfg::XSTAGE;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(packed + NP * Cfg::P_BYTES);
+    uint8_t *ytile = packed + NP * Cfg::P_BYTES;            // 2 x [32][128] 16-bit, epilogue staging for the TMA store
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ytile + Cfg::EPI_BYTES);
     uint64_t *full_x = bars;                     // [XS]  leader's copy collects both CTAs' TMA bytes
     uint64_t *empty_x = full_x + XS;             // [XS]  multicast tcgen05.commit
     uint64_t *full_p = empty_x + XS;             // [NP]  packed span landed (local)
@@ -257,16 +259,16 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 const int nkb = w.nspans * 4 + w.lora;
                 // accumulator slot(s) of this item must have been drained by the epilogue
                 if constexpr (ACCS == 1) {
-                    mbar_wait_cluster(&tmem_empty[ti & 1], (uint32_t)(((ti >> 1) & 1) ^ 1));
+                    mbar_wait(&tmem_empty[ti & 1], (uint32_t)(((ti >> 1) & 1) ^ 1));
                 } else {
-                    mbar_wait_cluster(&tmem_empty[0], (uint32_t)((ti & 1) ^ 1));
-                    mbar_wait_cluster(&tmem_empty[1], (uint32_t)((ti & 1) ^ 1));
+                    mbar_wait(&tmem_empty[0], (uint32_t)((ti & 1) ^ 1));
+                    mbar_wait(&tmem_empty[1], (uint32_t)((ti & 1) ^ 1));
                 }
                 g2_fence_after();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int sx = it % XS, sa = it % AST;
-                    mbar_wait_cluster(&full_x[sx], (uint32_t)((it / XS) & 1));
-                    mbar_wait_cluster(&full_a2[sa], (uint32_t)((it / AST) & 1));
+                    mbar_wait(&full_x[sx], (uint32_t)((it / XS) & 1));
+                    mbar_wait(&full_a2[sa], (uint32_t)((it / AST) & 1));
                     g2_fence_after();
                     const uint32_t x_addr = smem_u32(xt + sx * Cfg::XSTAGE);
                     const uint32_t a_col = tmem_base + (uint32_t)(TM::A_BASE + sa * 32);
@@ -302,7 +304,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_wait(&full_a[sa], (uint32_t)((it / AST) & 1));
                     g2_fence_after();
                     g2_fence_before();
-                    mbar_arrive_cluster(mapa_u32(smem_u32(&full_a2[sa]), 0));
+                    mbar_arrive_remote(mapa_u32(smem_u32(&full_a2[sa]), 0));
                 }
             }
         }
@@ -372,11 +374,16 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         }
     } else if (warp >= kG4EpiWarp0) {
         // ===================== epilogue: D[feature (lane), token (column)] -> Y[token, feature]
+        // A TMEM lane is a feature, so a thread holds 32 consecutive TOKENS of one feature.  The four epilogue warps (lane
+        // quadrants = 128 consecutive features) transpose through a [32 tokens][128 features] shared-memory tile (2-byte
+        // stores, lanes contiguous: conflict free) and ONE bulk tensor store per tile writes 32 token rows x 256 contiguous
+        // bytes (the TMA engine clips the M / N edges); two tiles alternate so the store of block b overlaps block b+1.
         const int quad = warp & 3;
+        const int et = threadIdx.x - kG4EpiWarp0 * 32;          // 0..127
         const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
         const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
-        int ti = 0;
+        int ti = 0, blk = 0;
         for (int item = pair; item < p.n_items; item += n_pairs, ++ti) {
             const G4Item w = g4_item(p, item);
             const long long n = (long long)w.ftile * 256 + rank * 128 + quad * 32 + lane;      // this thread's feature
@@ -387,7 +394,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int a = 0; a < ACCS; ++a) {
                 const int slot = ACCS == 1 ? (ti & 1) : a;
                 const uint32_t par = ACCS == 1 ? (uint32_t)((ti >> 1) & 1) : (uint32_t)(ti & 1);
-                mbar_wait_cluster(&tmem_full[slot], par);
+                mbar_wait(&tmem_full[slot], par);
                 g2_fence_after();
                 const long long m_base = (long long)w.ttile * (TT * ACCS) + a * TT;
 #pragma unroll 1
@@ -400,22 +407,38 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (n_ok && m_base + c0 + j < p.M) dst[(long long)j * p.N] = __uint_as_float(r[j]);
-                    } else {
-                        uint16_t *dst = reinterpret_cast<uint16_t *>(p.Y) + (m_base + c0) * p.ldy + n;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]) + bv;
-                            uint16_t hb;
-                            if constexpr (ACT == kBF16) hb = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-                            else hb = __half_as_ushort(__float2half_rn(v));
-                            if (n_ok && m_base + c0 + j < p.M) dst[(long long)j * p.ldy] = hb;
-                        }
+                        continue;
                     }
+                    if (m_base + c0 >= p.M) continue;        // block-uniform: whole 32-token block past the end
+                    uint8_t *tile = ytile + (blk & 1) * (32 * 128 * 2);
+                    // the bulk store issued from this tile two blocks ago must have finished READING it
+                    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const uint32_t trow = smem_u32(tile) + (uint32_t)(et * 2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]) + bv;
+                        uint16_t hb;
+                        if constexpr (ACT == kBF16) hb = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+                        else hb = __half_as_ushort(__float2half_rn(v));
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(trow + (uint32_t)(j * 256)), "h"(hb) : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (et == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&tmY)),
+                                     "r"(smem_u32(tile)), "r"((int)(w.ftile * 256 + rank * 128)), "r"((int)(m_base + c0))
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++blk;
                 }
                 g2_fence_before();
-                mbar_arrive_cluster(slot ? empty_remote1 : empty_remote0);
+                mbar_arrive_remote(slot ? empty_remote1 : empty_remote0);
             }
         }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all output tiles have left shared memory and landed
     }
 
     g2_fence_before();
@@ -538,6 +561,16 @@ static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
     if (!g2_make_map(&tmX, a.X, a.M, a.K, a.ldx, ACT, TT / 2)) return GGUFB200_E_CUDA;
     tmT = tmX;
     if (a.loraT && !g2_make_map(&tmT, a.loraT, a.M, 64, a.ldt, ACT, TT / 2)) return GGUFB200_E_CUDA;
+    CUtensorMap tmY;
+    {   // output: [M tokens, N features] 16-bit, stored in boxes of 32 tokens x 128 features, no swizzle
+        cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.M};
+        cuuint64_t strides[1] = {(cuuint64_t)a.ldy * 2};
+        cuuint32_t box[2] = {128u, 32u};
+        cuuint32_t estr[2] = {1, 1};
+        if (fn(&tmY, ACT == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.Y, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return GGUFB200_E_CUDA;
+    }
     const long long row_bytes = a.K / Q::BS * Q::TS;
     if (a.Wspan) {
         tmW = tmX;   // unused by the kernel in this mode
@@ -582,7 +615,7 @@ static int g4_launch(const G4Args &a, const G4Plan &pl, float *partial)
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmT, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+    return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmT, tmY, p) == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 
 template <class Q, int ACT, int PROD> static int g4_tiles(const G4Args &a, const G4Plan &pl, float *partial)

@@ -46,6 +46,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrive with the default semantics (release at CTA scope), the form CUTLASS uses for remote barrier arrives.  When the
+// payload handed over lives in tensor memory (ordered by tcgen05.fence + the barrier itself), no cluster-scope memory release is
+// needed -- and the cluster-scope form above costs a full cluster fence (~0.7 us measured on the relay thread of gemm4: it capped
+// the kernel at one k-block per 0.75-0.85 us whatever the MMA size was).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // TMA 2-D tile load whose completion bytes are credited to an mbarrier that may live in the PEER CTA of the pair

@@ -23,7 +23,7 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
+ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_spans", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
 side = torch.cuda.Stream()
 for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
     qt = gguf.GGMLQuantizationType[qname]
@@ -35,6 +35,7 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
             raw = torch.from_numpy(oracle.random_blocks(int(qt), 1 << 14, seed=c, scale=0.02))
             reps = (N * K // bs + (1 << 14) - 1) // (1 << 14)
             ws.append(raw.repeat(reps, 1)[: N * K // bs].reshape(N, K // bs * ts).contiguous().to(dev))
+        spans = [ops.span_layout(ops.GGMLTensor(w, tensor_type=qt, tensor_shape=torch.Size((N, K))), w) for w in ws]
         for M in (1, 4, 8):
             x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -43,8 +44,12 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
                 wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
 
                 def launch(i, st):
-                    rc = L.ggufb200_linear(int(qt), ws[i % copies].data_ptr(), N, K, x.data_ptr(), M, K, 1, 0, None, 0, y.data_ptr(), N,
-                                           wsb.data_ptr(), need, algo, st)
+                    if name == "tmem_spans":
+                        rc = L.ggufb200_linear_spans(int(qt), ws[i % copies].data_ptr(), spans[i % copies].data_ptr(), N, K, x.data_ptr(), M, K, 1, 0,
+                                                     None, 0, y.data_ptr(), N, wsb.data_ptr(), need, algo, st)
+                    else:
+                        rc = L.ggufb200_linear(int(qt), ws[i % copies].data_ptr(), N, K, x.data_ptr(), M, K, 1, 0, None, 0, y.data_ptr(), N,
+                                               wsb.data_ptr(), need, algo, st)
                     assert rc == 0, rc
                 st0 = torch.cuda.current_stream().cuda_stream
                 for i in range(6):

@@ -96,6 +96,8 @@ def main():
                 "tmem384": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE384 | nosplit),
                 "tmem_exact": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W | nosplit),
                 "tmem384_exact": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W | lib.FLAG_TILE384 | nosplit),
+                "tmem_spans": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | nosplit, use_spans=True),
+                "tmem384_spans": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE384 | nosplit, use_spans=True),
                 "tmem_generic": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_GENERIC | nosplit),
                 "fused": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_MMA | nosplit),
                 "auto": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_AUTO),
