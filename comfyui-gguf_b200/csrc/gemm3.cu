@@ -104,27 +104,35 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one thread)
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues (operands stay in uniform
+        // registers; issued from inside `if (lane == 0)` every tcgen05.mma operand went through an ELECT / R2UR.BROADCAST loop)
+        if (leader) {
             constexpr uint32_t idesc = g2_idesc<ACT, BN>();
+            const bool elected = elect_one_sync();
+            const uint64_t desc0 = g2_desc_sw128(smem_u32(tiles));
             int it = 0, ti = 0;
             for (int tile = pair; tile < p.n_tiles; tile += n_pairs, ++ti) {
                 const int ab = ti & 1;
-                mbar_wait_cluster(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));   // epilogue drained this buffer
+                mbar_wait(&tmem_empty[ab], (uint32_t)(((ti >> 1) & 1) ^ 1));   // epilogue drained this buffer
                 g2_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+                int s = it % kG3Stages;
+                uint32_t par = (uint32_t)((it / kG3Stages) & 1);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % kG3Stages;
-                    mbar_wait_cluster(&full[s], (uint32_t)((it / kG3Stages) & 1));
+                    mbar_wait(&full[s], par);
                     g2_fence_after();
-                    const uint32_t a_addr = smem_u32(tiles + s * kG3StageBytes);
-                    const uint32_t b_addr = a_addr + 128 * 128;
+                    if (elected) {
+                        const uint64_t da = desc0 + (uint64_t)((uint32_t)(s * kG3StageBytes) >> 4);
 #pragma unroll
-                    for (int j = 0; j < kG2BK / 16; ++j)
-                        umma_f16_pair(tacc, g2_desc_sw128(a_addr + j * 32), g2_desc_sw128(b_addr + j * 32), idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                    umma_commit_pair(&empty[s]);
+                        for (int j = 0; j < kG2BK / 16; ++j)
+                            umma_f16_pair(tacc, da + (uint64_t)((j * 32) >> 4), da + (uint64_t)((128 * 128 + j * 32) >> 4), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_commit_pair(&empty[s]);
+                    }
+                    __syncwarp();
+                    if (++s == kG3Stages) { s = 0; par ^= 1u; }
                 }
-                umma_commit_pair(&tmem_full[ab]);
+                if (elected) umma_commit_pair(&tmem_full[ab]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 4 + kG3EpiWarps) {
@@ -139,7 +147,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int ab = ti & 1;
             const long long m_base = (long long)(tile % p.tiles_m) * 256 + rank * 128 + quad * 32;
             const long long n0 = (long long)(tile / p.tiles_m) * BN;
-            mbar_wait_cluster(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
+            mbar_wait(&tmem_full[ab], (uint32_t)((ti >> 1) & 1));
             g2_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * BN);
 #pragma unroll 1
@@ -179,7 +187,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             // this thread's TMEM reads of buffer `ab` are complete (tcgen05.wait::ld above): hand it back to the MMA issuer
             g2_fence_before();
-            mbar_arrive_cluster(ab ? empty_remote1 : empty_remote0);
+            mbar_arrive_remote(ab ? empty_remote1 : empty_remote0);
         }
     }
 

@@ -20,7 +20,7 @@
 // Warp roles per CTA (768 threads):
 //   0      TMA producer, activations: X tile [ACCS x TT/2 tokens x 64 k] per k-block, 128B-swizzled, bytes of both CTAs are
 //          credited to the leader's full_x barrier (.cta_group::2)
-//   1      MMA issuer (leader CTA, one thread)
+//   1      MMA issuer (leader CTA; warp-uniform loop, one elected lane issues)
 //   2      TMEM allocation; relay: forwards "this CTA's A stage is complete" to the leader with one cluster-scope arrive
 //   3      TMA producer, packed weight: this CTA's 128 rows of one 256-wide K-span per copy (2-D tensor map over the raw
 //          bytes, or one bulk copy from the re-packed span-major layout), ring of NP buffers
@@ -250,9 +250,15 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one thread)
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (leader CTA).  The WHOLE warp runs the loop with warp-uniform control flow and one
+        // elected lane issues: the addresses / descriptors are then provably uniform and stay in uniform registers.  (Issued
+        // from inside `if (lane == 0)` every operand of every tcgen05.mma went through an ELECT / R2UR.BROADCAST loop: ~15
+        // instructions per MMA on one thread -- ncu showed the issuing thread, not the tensor pipe, pacing the kernel:
+        // 58 % tensor-pipe-active with the producers idle 55 % of the time, profiles/r02_gemm4_v2_tile384_ncu.txt.)
+        if (leader) {
             constexpr uint32_t idesc = g4_idesc<ACT, TT, WCAST>();
+            const bool elected = elect_one_sync();
+            const uint64_t desc0 = g2_desc_sw128(smem_u32(xt));          // descriptor of stage 0; later stages / k steps add (bytes >> 4)
             int it = 0, ti = 0;
             for (int item = pair; item < p.n_items; item += n_pairs, ++ti) {
                 const G4Item w = g4_item(p, item);
@@ -265,31 +271,39 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_wait(&tmem_empty[1], (uint32_t)((ti & 1) ^ 1));
                 }
                 g2_fence_after();
+                const uint32_t d_col = tmem_base + (uint32_t)((ACCS == 1 ? (ti & 1) : 0) * TT);
+                int sx = it % XS, sa = it % AST;
+                uint32_t px = (uint32_t)((it / XS) & 1), pa = (uint32_t)((it / AST) & 1);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int sx = it % XS, sa = it % AST;
-                    mbar_wait(&full_x[sx], (uint32_t)((it / XS) & 1));
-                    mbar_wait(&full_a2[sa], (uint32_t)((it / AST) & 1));
+                    mbar_wait(&full_x[sx], px);
+                    mbar_wait(&full_a2[sa], pa);
                     g2_fence_after();
-                    const uint32_t x_addr = smem_u32(xt + sx * Cfg::XSTAGE);
-                    const uint32_t a_col = tmem_base + (uint32_t)(TM::A_BASE + sa * 32);
+                    if (elected) {
+                        const uint64_t dx = desc0 + (uint64_t)((uint32_t)(sx * Cfg::XSTAGE) >> 4);
+                        const uint32_t a_col = tmem_base + (uint32_t)(TM::A_BASE + sa * 32);
 #pragma unroll
-                    for (int j = 0; j < kG2BK / 16; ++j) {
+                        for (int j = 0; j < kG2BK / 16; ++j) {
 #pragma unroll
-                        for (int a = 0; a < ACCS; ++a) {
-                            const int slot = ACCS == 1 ? (ti & 1) : a;
-                            g4_umma_ts(tmem_base + (uint32_t)(slot * TT), a_col + (uint32_t)(j * 8),
-                                       g2_desc_sw128(x_addr + a * Cfg::X_BYTES + j * 32), idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            for (int a = 0; a < ACCS; ++a)
+                                g4_umma_ts(d_col + (uint32_t)(a * TT), a_col + (uint32_t)(j * 8), dx + (uint64_t)((a * Cfg::X_BYTES + j * 32) >> 4), idesc,
+                                           (kb > 0 || j > 0) ? 1u : 0u);
                         }
+                        umma_commit_pair(&empty_x[sx]);
+                        umma_commit_pair(&empty_a[sa]);
                     }
-                    umma_commit_pair(&empty_x[sx]);
-                    umma_commit_pair(&empty_a[sa]);
+                    __syncwarp();
+                    if (++sx == XS) { sx = 0; px ^= 1u; }
+                    if (++sa == AST) { sa = 0; pa ^= 1u; }
                 }
-                if constexpr (ACCS == 1) {
-                    umma_commit_pair(&tmem_full[ti & 1]);
-                } else {
-                    umma_commit_pair(&tmem_full[0]);
-                    umma_commit_pair(&tmem_full[1]);
+                if (elected) {
+                    if constexpr (ACCS == 1) {
+                        umma_commit_pair(&tmem_full[ti & 1]);
+                    } else {
+                        umma_commit_pair(&tmem_full[0]);
+                        umma_commit_pair(&tmem_full[1]);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 2) {

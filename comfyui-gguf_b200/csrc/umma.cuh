@@ -23,6 +23,17 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
     return r;
 }
+// one lane of a CONVERGED warp (the same lane every time)
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
