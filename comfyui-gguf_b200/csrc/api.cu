@@ -88,9 +88,8 @@ static int device_check()
 }
 
 // ------------------------------------------------------------------ route selection
-// Measured on B200 (profiles/):  the TMEM-fed fused kernel serves every M when its contract is acceptable (default);
-// the reference-exact routes keep the round-1 thresholds: M <= 8 mma.sync GEMV, short activations split-K fused through
-// shared memory, long activations dequant once into the workspace + dense tcgen05 GEMM.
+// Fallback thresholds (round 1) for weights the TMEM-fed kernel cannot stage: short activations split-K fused through shared
+// memory, long activations dequant once into the workspace + dense tcgen05 GEMM.
 static bool exact_prefers_fused(long long M, long long N, long long K)
 {
     if ((K % 64) != 0) return false;
@@ -112,6 +111,7 @@ static int g4_flags(int flags)
     int f = (flags & GGUFB200_FLAG_GENERIC) ? 0 : 1;
     if (flags & GGUFB200_FLAG_EXACT_W) f |= 16;       // hand-written producers that keep the reference's rounding sequence
     if (flags & GGUFB200_FLAG_TILE384) f |= 2;
+    if (flags & GGUFB200_FLAG_TILE192) f |= 32;
     if (flags & GGUFB200_FLAG_NOSPLIT) f |= 4;
     return f;
 }
@@ -136,10 +136,14 @@ static Route pick_route(int type, const void *W, long long M, long long N, long 
     const bool fusable = fused_type(type) && math == kF16 && (K % 64) == 0 && (N % 8) == 0;
     Route r{algo, 0};
     if (algo == GGUFB200_ALGO_AUTO) {
-        const bool exact = (flags & GGUFB200_FLAG_EXACT_W) != 0 || math != kF16;
+        // Measured on B200 (profiles/r02_bench_linear_*.log, r02_bench_gemv*.log).  The TMEM-fed fused kernel is the route for
+        // every M > 8 (with EXACT_W it runs the reference-sequence producers at the same speed: it is tensor-pipe bound) and for
+        // M <= 8 on large weights; the mma.sync GEMV keeps small weights at M <= 8 (its fixed cost is lower).  A math dtype other
+        // than fp16 means the reference's own sequence in that dtype: standalone dequant + dense GEMM (or the GEMV).
+        const bool tmem_ok = w_ok && fused_type(type) && math == kF16 && (N % 8) == 0 && (have_spans || gemm4_supported(type, W, N, K));
         if (!w_ok) r.algo = GGUFB200_ALGO_DEQUANT_MMA;
-        else if (!exact && fused_type(type) && (N % 8) == 0 && (have_spans || gemm4_supported(type, W, N, K))) r.algo = GGUFB200_ALGO_FUSED_TMEM;
-        else if (M <= gemv_max_m()) r.algo = GGUFB200_ALGO_GEMV;
+        else if (M <= gemv_max_m()) r.algo = (tmem_ok && (long long)N * K >= (40ll << 20)) ? GGUFB200_ALGO_FUSED_TMEM : GGUFB200_ALGO_GEMV;
+        else if (tmem_ok) r.algo = GGUFB200_ALGO_FUSED_TMEM;
         else if (fusable && (exact_prefers_fused(M, N, K) || ws_avail < dense)) r.algo = GGUFB200_ALGO_FUSED_MMA;
         else r.algo = GGUFB200_ALGO_DEQUANT_MMA;
     }

@@ -471,47 +471,72 @@ struct G4Plan {
 
 // Tiling: token tile TT in {32, 128, 192}; ACCS = 2 (384-token items) when asked for; K split into ranges of whole spans
 // when the output has fewer items than SM pairs (short activations; every packed byte is still read exactly once).
+// Tiling by a small cost model (cycles per SM pair): an item of `tile` tokens x `kb` k-blocks costs
+//   kb * max(2 * tile, 400)   (UMMA 256 x tile x 64 = 2 * tile cycles; ~400 cycles is what the dequant producers need per k-block)
+//   + 3000 (pipeline fill + drain) + 1500 if the epilogue is exposed (384-token items)
+// and the kernel runs ceil(items / pairs) rounds of the most expensive item.  Candidates: token tile 32 (M <= 32) / 128 / 192 /
+// 384, K cut into 1..32 ranges of whole spans when a workspace for the fp32 partials is available (finalize pass charged at
+// 16 bytes / cycle / SM: the slices stay L2 resident).  want_accs: 0 = let the model decide, 1 = force 192-token items, 2 = force 384-token items.
 static G4Plan g4_plan(long long M, long long N, long long K, size_t ws_bytes, int want_accs, bool allow_split = true)
 {
-    G4Plan pl{};
     const int pairs = sm_count() / 2;
-    pl.ftiles = (int)((N + 255) / 256);
-    pl.accs = 1;
-    if (M <= 32) pl.tt = 32;
-    else if (M <= 128 || (M <= 1024 && (M + 127) / 128 * 128 < (M + 191) / 192 * 192)) pl.tt = 128;
-    else pl.tt = 192;
-    if (pl.tt == 192 && want_accs == 2 && M > 192) pl.accs = 2;
-    const int tile_tokens = pl.tt * pl.accs;
-    pl.ttiles = (int)((M + tile_tokens - 1) / tile_tokens);
+    const int ftiles = (int)((N + 255) / 256);
     const int spans = (int)((K + 255) / 256);
-    const long long tiles = (long long)pl.ftiles * pl.ttiles;
-    int s = 1;
     const size_t slice = (size_t)M * (size_t)N * 4;
-    if (allow_split && tiles < pairs && slice > 0 && ws_bytes >= 2 * slice) {
-        long long want = pairs / tiles;
-        if (want > spans) want = spans;
-        if (want > 32) want = 32;
-        if (want > (long long)(ws_bytes / slice)) want = (long long)(ws_bytes / slice);
-        if (want >= 2) s = (int)want;
+    int max_s = 1;
+    if (allow_split && slice > 0 && ws_bytes >= 2 * slice) {
+        long long cap = (long long)(ws_bytes / slice);
+        max_s = (int)(cap < 32 ? cap : 32);
+        if (max_s > spans) max_s = spans;
     }
-    pl.spans_per_split = (spans + s - 1) / s;
-    pl.splits = (spans + pl.spans_per_split - 1) / pl.spans_per_split;
-    pl.n_items = (int)(tiles * pl.splits);
-    return pl;
+    struct Cand { int tt, accs; };
+    Cand cands[4];
+    int nc = 0;
+    if (M <= 32) cands[nc++] = {32, 1};
+    else {
+        if (want_accs == 0 || M <= 192) cands[nc++] = {128, 1};
+        if (want_accs != 2 || M <= 192) cands[nc++] = {192, 1};
+        if (want_accs != 1 && M > 192) cands[nc++] = {192, 2};
+    }
+    G4Plan best{};
+    double best_cost = 0;
+    for (int c = 0; c < nc; ++c) {
+        const int tile = cands[c].tt * cands[c].accs;
+        const int ttiles = (int)((M + tile - 1) / tile);
+        const long long tiles = (long long)ftiles * ttiles;
+        for (int s = 1; s <= max_s; ++s) {
+            const int per = (spans + s - 1) / s;
+            const int splits = (spans + per - 1) / per;
+            if (splits != s) continue;                                  // same split count as a smaller s: already evaluated
+            const long long items = tiles * splits;
+            const long long rounds = (items + pairs - 1) / pairs;
+            const double t_kb = 2.0 * tile > 400.0 ? 2.0 * tile : 400.0;
+            double cost = (double)rounds * (4.0 * per * t_kb + 3000.0 + (cands[c].accs == 2 ? 1500.0 : 0.0));
+            if (splits > 1) cost += (double)(splits + 1) * (double)slice / (16.0 * 2 * pairs) + 6000.0;   // partial stores + finalize pass (L2 resident) + its launch
+            if (best.n_items == 0 || cost < best_cost * 0.98) {         // prefer the earlier (simpler) candidate on near ties
+                best_cost = cost;
+                best.tt = cands[c].tt; best.accs = cands[c].accs; best.splits = splits; best.spans_per_split = per;
+                best.ttiles = ttiles; best.ftiles = ftiles; best.n_items = (int)items;
+            }
+        }
+    }
+    return best;
 }
 
 constexpr size_t kG4SplitWsCap = 64u << 20;
 
-// flags: bit 1 (2) = 384-token items, bit 2 (4) = no split-K
+// flags: bit 1 (2) = force 384-token items, bit 5 (32) = force 192-token items, bit 2 (4) = no split-K
+static int g4_want_accs(int flags) { return (flags & 2) ? 2 : ((flags & 32) ? 1 : 0); }
+
 size_t gemm4_workspace(long long M, long long N, long long K, int flags)
 {
-    const G4Plan pl = g4_plan(M, N, K, kG4SplitWsCap, (flags & 2) ? 2 : 1, !(flags & 4));
+    const G4Plan pl = g4_plan(M, N, K, kG4SplitWsCap, g4_want_accs(flags), !(flags & 4));
     return pl.splits > 1 ? (size_t)pl.splits * (size_t)M * (size_t)N * 4 : 0;
 }
 
 void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items)
 {
-    const G4Plan pl = g4_plan(M, N, K, ws_bytes > kG4SplitWsCap ? kG4SplitWsCap : ws_bytes, (flags & 2) ? 2 : 1, !(flags & 4));
+    const G4Plan pl = g4_plan(M, N, K, ws_bytes > kG4SplitWsCap ? kG4SplitWsCap : ws_bytes, g4_want_accs(flags), !(flags & 4));
     *tile_tokens = pl.tt * pl.accs;
     *splits = pl.splits;
     *spans_per_split = pl.spans_per_split;
@@ -678,13 +703,13 @@ template <class Q> static bool g4_canonical_ok(const void *W, long long K)
 }
 
 // flags: bits 0 / 4 = producers (1: hand-written, fused multiply-add; 17: hand-written, reference sequence; 0: generic),
-// bit 1 = 384-token items (ACCS = 2), bit 2 = no split-K
+// bit 1 = force 384-token items (ACCS = 2), bit 5 = force 192-token items, bit 2 = no split-K
 int gemm4_fused_dispatch(int type, const void *W, const void *Wspan, long long span_stride, long long N, long long K, const void *X, long long M,
                          long long ldx, int act_dtype, const void *bias, int bias_dtype, void *Y, long long ldy, void *ws, size_t ws_bytes,
                          int flags, const void *loraT, long long ldt, const void *loraU, cudaStream_t st)
 {
     if (N % 8 != 0 || K % 8 != 0) return GGUFB200_E_UNSUPPORTED;
-    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, (flags & 1) ? ((flags & 16) ? 2 : 1) : 0, (flags & 2) ? 2 : 1, (flags & 4) ? 1 : 0,
+    G4Args a{W, Wspan, span_stride, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, ws_bytes, (flags & 1) ? ((flags & 16) ? 2 : 1) : 0, (flags & 2) ? 2 : ((flags & 32) ? 1 : 0), (flags & 4) ? 1 : 0,
              loraT, ldt, loraU, st};
 #define GGUFB200_G4_CASE(T)                                                                    \
     case T:                                                                                    \

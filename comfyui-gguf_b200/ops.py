@@ -399,13 +399,15 @@ class GGMLOps(comfy_ops.manual_cast):
         lora_side_gemm = True
 
         # Numerics contract of the packed-weight Linear (include/ggufb200.h GGUFB200_FLAG_EXACT_W):
-        #   "fast"   (default) AUTO may take the TMEM-fed fused kernel: integer unpack bit-exact, one fused multiply-add per
-        #            element for the hot formats, fp16 W fed to the tensor core without the cast to bf16
-        #   "exact"  only routes whose weight operand is bit-identical to the reference's `dequantize_tensor(...).to(dtype)`
-        linear_numerics = "fast"
+        #   "exact"  (default) the weight operand of every route is bit-identical to the reference's
+        #            `dequantize_tensor(...).to(dtype)`; only the fp32 summation order differs (<= 1e-3, measured <= 3e-4)
+        #   "fast"   the TMEM-fed kernel runs its fused-multiply-add producers (Q4_K / Q5_K: one rounding instead of two per
+        #            element; 1e-3 for fp16 activations, 8e-3 for bf16) -- only pays off where the producers, not the tensor
+        #            pipe, bound the kernel (small M)
+        linear_numerics = "exact"
         # Weights whose canonical rows the TMA engine cannot stage (Q2_K / Q3_K / Q6_K / IQ4_XS, Q8_0 at K = 2432 ...) get a
         # re-packed span-major shadow copy on first use (one extra copy of the packed bytes in HBM, csrc/repack.cu) so that
-        # they too run on the TMEM-fed kernel; False keeps them on the reference-exact routes.
+        # they too run on the TMEM-fed kernel; False keeps them on the round-1 routes (smem-fed fused / dequant + dense GEMM).
         repack_spans = True
 
         def _fused_ok(self, input):
@@ -493,19 +495,19 @@ class GGMLOps(comfy_ops.manual_cast):
                 elif M <= GEMV_MAX_M or N % 8 == 0:                    # (the M <= 8 kernel stores per element: any N)
                     math = math_code(self.dequant_dtype, input.dtype)
                     algo, spans = _lib.ALGO_AUTO, None
-                    if self.linear_numerics != "fast":
-                        algo |= _lib.FLAG_EXACT_W
-                    elif (self.repack_spans and resident and math == _F16_CODE and N % 8 == 0 and qtype != _Q.BF16
-                          and needs_span_layout(qtype, K)):
+                    exact = _lib.FLAG_EXACT_W if self.linear_numerics != "fast" else 0
+                    algo |= exact
+                    if (self.repack_spans and resident and math == _F16_CODE and N % 8 == 0 and qtype != _Q.BF16
+                            and needs_span_layout(qtype, K) and (M > GEMV_MAX_M or N * K >= (40 << 20))):
                         spans = span_layout(w, wraw)                   # cached on the tensor after the first forward
-                        algo = _lib.ALGO_FUSED_TMEM
+                        algo = _lib.ALGO_FUSED_TMEM | exact
                     lora = None
-                    if (terms and self.lora_in_kernel and self.linear_numerics == "fast" and math == _F16_CODE and N % 8 == 0
+                    if (terms and self.lora_in_kernel and math == _F16_CODE and N % 8 == 0
                             and qtype != _Q.BF16 and sum(d.shape[0] for _s, _u, d in terms) <= LORA_MAX_RANK
                             and (spans is not None or not needs_span_layout(qtype, K))):
                         down_pad, u_pad = self._lora_operands(terms, dev, input.dtype)
                         lora = (linear_dense(input.reshape(-1, K), down_pad), u_pad)       # T = x * down^T, [M, 64]
-                        algo = _lib.ALGO_FUSED_TMEM
+                        algo = _lib.ALGO_FUSED_TMEM | exact
                     y = _launch_linear(input, wraw, qtype, N, K, b, math, algo, spans, lora)
                     if lora is not None:
                         return y

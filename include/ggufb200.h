@@ -62,20 +62,21 @@ extern "C" {
 #define GGUFB200_ALGO_GEMV 1        /* M <= 8: fused dequant + mma.sync dot products, W bit-identical to the reference */
 #define GGUFB200_ALGO_FUSED_MMA 2   /* fused dequant -> shared memory -> tcgen05.mma (W bit-identical to the reference) */
 #define GGUFB200_ALGO_DEQUANT_MMA 3 /* dequant into the caller's workspace, then the tcgen05 GEMM on it (W bit-identical) */
-#define GGUFB200_ALGO_FUSED_TMEM 4  /* fused dequant -> TENSOR MEMORY -> tcgen05.mma, any M (persistent; the AUTO default) */
+#define GGUFB200_ALGO_FUSED_TMEM 4  /* fused dequant -> TENSOR MEMORY -> tcgen05.mma, any M (persistent; what AUTO picks for M > 8) */
 #define GGUFB200_ALGO_MASK 0xFF
 
 /* Per-call switches (no process-wide state):
- *   EXACT_W    AUTO only picks routes whose weight operand is bit-identical to what the reference hands to F.linear
- *              (dequant.py float sequence with per-op rounding, then the cast to the activation dtype).  Without it AUTO
- *              prefers GGUFB200_ALGO_FUSED_TMEM with its hand-written producers, whose contract is: integer unpack
- *              bit-exact; sub-block scale products as the reference; for Q4_K / Q5_K the per-element float step is ONE
- *              fused multiply-add in fp16 (the correctly rounded value of the step) instead of multiply + subtract; then
- *              the reference's cast to the activation dtype.  The result is as close to the exact product as the
- *              reference's and within 1e-3 (fp16) / 8e-3 (bf16, = the same bound in bf16 ulps) of it.
- *   GENERIC    FUSED_TMEM: producers that follow the reference's rounding sequence op for op -> the weight operand is
- *              bit-identical to the reference's in fp16 AND bf16 (EXACT_W-compatible)
- *   TILE384    FUSED_TMEM: 384-token items (both accumulator slots per dequantised tile, epilogue not overlapped)
+ *   EXACT_W    the weight operand must be bit-identical to what the reference hands to F.linear (dequant.py float sequence with
+ *              per-op rounding, then the cast to the activation dtype): FUSED_TMEM then runs its reference-sequence
+ *              producers (same speed at large M: the kernel is tensor-pipe bound), every other route is exact anyway.
+ *              Without it FUSED_TMEM uses the `fast` producers, whose contract is: integer unpack bit-exact; sub-block scale
+ *              products as the reference; for Q4_K / Q5_K the per-element float step is ONE fused multiply-add in fp16 (the
+ *              correctly rounded value of the step) instead of multiply + subtract; then the reference's cast to the
+ *              activation dtype.  Result as close to the exact product as the reference's, within 1e-3 (fp16) / 8e-3
+ *              (bf16, = the same bound in bf16 ulps) of the reference's.
+ *   GENERIC    FUSED_TMEM: functor producers that follow the reference's rounding sequence op for op (every format; also exact)
+ *   TILE384    FUSED_TMEM: force 384-token items (both accumulator slots per dequantised tile, epilogue not overlapped)
+ *   TILE192    FUSED_TMEM: force 192-token items (accumulator slots alternate between items); default: a cost model picks
  *   NOSPLIT    FUSED_MMA / FUSED_TMEM: never cut K into ranges
  *   UNSTAGED   FUSED_MMA: producers read packed rows from global memory instead of TMA-staged shared memory */
 #define GGUFB200_FLAG_EXACT_W 0x100
@@ -83,6 +84,7 @@ extern "C" {
 #define GGUFB200_FLAG_TILE384 0x400
 #define GGUFB200_FLAG_NOSPLIT 0x800
 #define GGUFB200_FLAG_UNSTAGED 0x1000
+#define GGUFB200_FLAG_TILE192 0x2000 /* FUSED_TMEM: force 192-token items (double-buffered accumulators); default: cost model */
 
 int ggufb200_version(void);
 const char *ggufb200_strerror(int rc);

@@ -100,23 +100,23 @@ def test_workspace_contract_follows_the_route(pkg):
     assert ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_MMA) == 16 * 64 * 512 * 4           # split-K: 16 slices
     assert ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_MMA | A.FLAG_NOSPLIT) == 0
     assert ws(q4k, 512, 3072, 12288, 1, A.ALGO_FUSED_MMA) == 6 * 512 * 3072 * 4       # 12 tiles of 512x256 -> 6 ranges
-    # AUTO, default contract: the TMEM-fed fused kernel for every M (K ranges only when items < SM pairs)
-    assert ws(q4k, 4608, 3072, 3072, 1, A.ALGO_AUTO) == 0
-    assert ws(q4k, 4, 3072, 3072, 1, A.ALGO_AUTO) == 6 * 4 * 3072 * 4
-    assert ws(q4k, 4, 18432, 3072, 1, A.ALGO_AUTO) == 0
-    assert ws(q4k, 64, 512, 4096, 1, A.ALGO_AUTO) == ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_TMEM) == 16 * 64 * 512 * 4
-    # AUTO restricted to reference-exact weights: GEMV / split-K fused / dequant+GEMM as in round 1
-    ex = A.ALGO_AUTO | A.FLAG_EXACT_W
-    assert ws(q4k, 4608, 3072, 3072, 1, ex) == 3072 * 3072 * 2
-    assert ws(q4k, 64, 512, 4096, 1, ex) == 16 * 64 * 512 * 4
-    assert ws(q4k, 4, 3072, 3072, 1, ex) == 0
+    # AUTO: the TMEM-fed fused kernel for every M > 8 and for M <= 8 on large weights (K ranges only when that beats idle SM
+    # pairs by the cost model); EXACT_W only changes its producers, never the route or the workspace
+    for flags in (0, A.FLAG_EXACT_W):
+        auto = A.ALGO_AUTO | flags
+        assert ws(q4k, 4608, 3072, 3072, 1, auto) == 0
+        assert ws(q4k, 4, 3072, 3072, 1, auto) == 0                                   # small weight at M <= 8: mma.sync GEMV
+        assert ws(q4k, 4, 18432, 3072, 1, auto) == 0                                  # large weight at M <= 8: TMEM kernel, 72 items, unsplit
+        assert ws(q4k, 64, 512, 4096, 1, auto) == ws(q4k, 64, 512, 4096, 1, A.ALGO_FUSED_TMEM) > 0
+        assert ws(q4k, 64, 512, 4096, 1, auto) % (64 * 512 * 4) == 0
+        assert ws(q4k, 64, 512, 4096, 1, auto | A.FLAG_NOSPLIT) == 0
     # a non-fp16 math dtype always means the reference's own sequence in that dtype: dequant + GEMM above the GEMV range
     wx = L.ggufb200_linear_workspace_ex
     assert wx(q4k, 4608, 3072, 3072, 1, 1, A.ALGO_AUTO) == 3072 * 3072 * 2
     assert wx(q4k, 64, 512, 4096, 1, 2, A.ALGO_AUTO) == 512 * 4096 * 2
     assert wx(q4k, 4, 3072, 3072, 1, 2, A.ALGO_AUTO) == 0
     assert wx(q4k, 64, 512, 4096, 1, 0, A.ALGO_AUTO) == ws(q4k, 64, 512, 4096, 1, A.ALGO_AUTO)
-    # formats / shapes the TMEM route cannot stage from the canonical rows fall back to the exact routes
+    # formats / shapes the TMEM route cannot stage from the canonical rows (no span-major copy at hand) fall back to round 1's routes
     assert ws(int(Q.Q6_K), 4608, 3072, 3072, 1, A.ALGO_AUTO) == 3072 * 3072 * 2       # 210-byte blocks
     assert ws(int(Q.Q8_0), 4608, 7296, 2432, 1, A.ALGO_AUTO) == 7296 * 2432 * 2       # 2584-byte rows
     # row gather: K must be a multiple of the block size

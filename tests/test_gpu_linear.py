@@ -2,9 +2,10 @@
 
 Tolerance (written here, from BASELINE.json north_star): ||y - y_ref||_F / ||y_ref||_F <= 1e-3 for fp16/bf16 Linear
 outputs; y_ref is the unmodified reference's GGMLOps.Linear output (golden files) or the CPU oracle.
-Every layer-level test runs under both numerics contracts of GGMLOps.Linear (`linear_numerics`): "exact" (weight operand
-bit-identical to the reference's: 1e-3 in every dtype) and "fast" (the default; TMEM-fed fused kernel: 1e-3 for fp16
-activations, 8e-3 = the same bound in bf16 ulps for bf16 activations -- see tests/test_gpu_gemm.py and DESIGN.md section 3)."""
+Every layer-level test runs under both numerics contracts of GGMLOps.Linear (`linear_numerics`): "exact" (the default: weight
+operand bit-identical to the reference's: 1e-3 in every dtype) and "fast" (fused-multiply-add producers on the TMEM-fed
+kernel: 1e-3 for fp16 activations, 8e-3 = the same bound in bf16 ulps for bf16 activations -- see tests/test_gpu_gemm.py and
+DESIGN.md section 3)."""
 import os
 
 import numpy as np

@@ -15,7 +15,7 @@ PAIRS = 74          # 148 SMs (sm_count() reports 148 without a device as well)
 CAP = 64 << 20
 
 
-FUSED_MMA, FUSED_TMEM, NOSPLIT, TILE384 = 2, 4, 0x800, 0x400
+FUSED_MMA, FUSED_TMEM, NOSPLIT, TILE384, TILE192 = 2, 4, 0x800, 0x400, 0x2000
 
 
 def _plan(L, qt, M, N, K, ws, algo=FUSED_MMA):
@@ -92,17 +92,23 @@ def _check_tmem(L, M, N, K, ws, flags=0):
     tiles = -(-M // tokens) * -(-N // 256)
     assert items == tiles * ranges
     if ranges > 1:
-        assert tiles < PAIRS and ranges <= 32
+        assert ranges <= 32
         assert ranges * M * N * 4 <= min(ws, CAP)
     if M <= 32:
         assert tokens == 32
+    if flags & TILE384 and M > 192:
+        assert tokens == 384
+    if flags & TILE192 and M > 192:
+        assert tokens == 192
     return ranges
 
 
 def test_known_tmem_plans(pkg):
     L = pkg.lib.lib()
-    assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM) == (0, (192, 1, 48, 48 * 24))      # Flux mlp.0: 1152 items
+    assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM | TILE192) == (0, (192, 1, 48, 48 * 24))      # Flux mlp.0: 1152 items
     assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM | TILE384) == (0, (384, 1, 48, 48 * 12))
+    assert _plan(L, Q.Q4_K, 4608, 12288, 3072, CAP, FUSED_TMEM) == (0, (384, 1, 48, 48 * 12))               # the cost model's pick
+    assert _plan(L, Q.Q4_K, 512, 3072, 12288, CAP, FUSED_TMEM) == (0, (192, 2, 96, 72))                      # 36 tiles x 2 K ranges
     assert _plan(L, Q.Q4_K, 1, 18432, 3072, CAP, FUSED_TMEM) == (0, (32, 1, 48, 72))               # modulation GEMV: one item per pair
     assert _plan(L, Q.Q4_K, 1, 3072, 3072, CAP, FUSED_TMEM) == (0, (32, 6, 8, 72))                 # 12 feature tiles x 6 K ranges
     assert _plan(L, Q.Q4_K, 1, 3072, 3072, 0, FUSED_TMEM)[1][1] == 1                               # no workspace: unsplit
@@ -111,11 +117,12 @@ def test_known_tmem_plans(pkg):
 
 
 @settings(max_examples=400, deadline=None)
-@given(M=st.integers(1, 5000), n8=st.integers(1, 3000), k64=st.integers(1, 300), ws_slices=st.integers(0, 40), t384=st.booleans())
-def test_tmem_plan_invariants(pkg, M, n8, k64, ws_slices, t384):
+@given(M=st.integers(1, 5000), n8=st.integers(1, 3000), k64=st.integers(1, 300), ws_slices=st.integers(0, 40),
+       tile=st.sampled_from([0, TILE384, TILE192]))
+def test_tmem_plan_invariants(pkg, M, n8, k64, ws_slices, tile):
     L = pkg.lib.lib()
     N, K = 8 * n8, 64 * k64
-    flags = TILE384 if t384 else 0
+    flags = tile
     ws = min(ws_slices * M * N * 4, 1 << 40)
     ranges = _check_tmem(L, M, N, K, ws, flags)
     need = L.ggufb200_linear_workspace(int(Q.Q4_K), M, N, K, 1, FUSED_TMEM | flags)
