@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libggufb200.so")
 _lib = None
 
 F16, BF16, F32 = 0, 1, 2
-ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA, ALGO_FUSED_TMEM = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA, ALGO_FUSED_TMEM, ALGO_GEMV_FAST = 0, 1, 2, 3, 4, 5
 ALGO_MASK = 0xFF
 # per-call switches OR-ed into `algo` (include/ggufb200.h)
 FLAG_EXACT_W, FLAG_GENERIC, FLAG_TILE384, FLAG_NOSPLIT, FLAG_UNSTAGED, FLAG_TILE192 = 0x100, 0x200, 0x400, 0x800, 0x1000, 0x2000

@@ -29,6 +29,9 @@ bool gemm4_supported(int type, const void *W, long long N, long long K);
 size_t gemm4_workspace(long long M, long long N, long long K, int flags);
 void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int flags, int *tile_tokens, int *splits, int *spans_per_split, int *items);
 int gemv_max_m();
+bool gemv2_supported(int type, const void *W, long long N, long long K, long long M);
+int gemv2_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype, const void *bias,
+                   int bias_dtype, void *Y, long long ldy, cudaStream_t st);
 size_t repack_bytes(int type, long long N, long long K, int *pitch, long long *span_stride);
 int repack_dispatch(int type, const void *W, long long N, long long K, void *out, cudaStream_t st);
 }  // namespace ggufb200
@@ -141,7 +144,9 @@ static Route pick_route(int type, const void *W, long long M, long long N, long 
         // M <= 8 on large weights; the mma.sync GEMV keeps small weights at M <= 8 (its fixed cost is lower).  A math dtype other
         // than fp16 means the reference's own sequence in that dtype: standalone dequant + dense GEMM (or the GEMV).
         const bool tmem_ok = w_ok && fused_type(type) && math == kF16 && (N % 8) == 0 && (have_spans || gemm4_supported(type, W, N, K));
+        const bool exact = (flags & GGUFB200_FLAG_EXACT_W) != 0 || math != kF16;
         if (!w_ok) r.algo = GGUFB200_ALGO_DEQUANT_MMA;
+        else if (M <= gemv_max_m() && !exact && gemv2_supported(type, W ? W : (const void *)16, N, K, M)) r.algo = GGUFB200_ALGO_GEMV_FAST;
         else if (M <= gemv_max_m()) r.algo = (tmem_ok && (long long)N * K >= (40ll << 20)) ? GGUFB200_ALGO_FUSED_TMEM : GGUFB200_ALGO_GEMV;
         else if (tmem_ok) r.algo = GGUFB200_ALGO_FUSED_TMEM;
         else if (fusable && (exact_prefers_fused(M, N, K) || ws_avail < dense)) r.algo = GGUFB200_ALGO_FUSED_MMA;
@@ -292,7 +297,7 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
     if (W_spans && !aligned16(W_spans)) return GGUFB200_E_ALIGN;
     const Route r = pick_route(ggml_type, W_packed, M, N, K, act_dtype, math_dtype, algo, ws_avail, W_spans != nullptr);
     // the small-M kernel stores per element: it only needs 2-byte aligned Y rows; every other route moves 16-byte vectors
-    const bool vec_y = r.algo != GGUFB200_ALGO_GEMV;
+    const bool vec_y = r.algo != GGUFB200_ALGO_GEMV && r.algo != GGUFB200_ALGO_GEMV_FAST;
     if (!aligned16(X) || (ldx % 8) != 0) return GGUFB200_E_ALIGN;
     if (vec_y && (!aligned16(Y) || (ldy % 8) != 0)) return GGUFB200_E_ALIGN;
     if (workspace && !aligned16(workspace) && r.ws) return GGUFB200_E_ALIGN;
@@ -307,6 +312,9 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
     switch (r.algo) {
     case GGUFB200_ALGO_GEMV:
         return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
+    case GGUFB200_ALGO_GEMV_FAST:
+        if (math_dtype != kF16 || (flags & GGUFB200_FLAG_EXACT_W)) return GGUFB200_E_UNSUPPORTED;
+        return gemv2_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
     case GGUFB200_ALGO_FUSED_MMA: {
         if (!fused_type(ggml_type)) return GGUFB200_E_UNSUPPORTED;
         int f = 0;

@@ -63,6 +63,8 @@ extern "C" {
 #define GGUFB200_ALGO_FUSED_MMA 2   /* fused dequant -> shared memory -> tcgen05.mma (W bit-identical to the reference) */
 #define GGUFB200_ALGO_DEQUANT_MMA 3 /* dequant into the caller's workspace, then the tcgen05 GEMM on it (W bit-identical) */
 #define GGUFB200_ALGO_FUSED_TMEM 4  /* fused dequant -> TENSOR MEMORY -> tcgen05.mma, any M (persistent; what AUTO picks for M > 8) */
+#define GGUFB200_ALGO_GEMV_FAST 5   /* M <= 8, Q4_K / Q5_K: integer patterns on mma.sync, sub-block scales applied to the partial sums
+                                       (W is never formed or rounded: the `fast` contract; AUTO picks it only without EXACT_W) */
 #define GGUFB200_ALGO_MASK 0xFF
 
 /* Per-call switches (no process-wide state):

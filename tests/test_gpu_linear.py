@@ -295,3 +295,41 @@ def test_conv2d_and_norms_with_quantised_parameters(pkg):
     gn.load_state_dict({"weight": wq, "bias": bq}, assign=True)
     xg = torch.randn(2, 64, 4, 4, device=DEV, generator=g).to(torch.float16)
     torch.testing.assert_close(gn(xg), torch.nn.functional.group_norm(xg, 8, wv.to(DEV).half(), bv.to(DEV).half(), gn.eps))
+
+
+# ---------------------------------------------------------------- K3 v2: integer patterns on mma.sync, scales applied to partial sums (csrc/gemv2.cu)
+@pytest.mark.parametrize("qt", [Q.Q4_K, Q.Q5_K], ids=lambda q: q.name)
+@pytest.mark.parametrize("dt,code", [(torch.bfloat16, 1), (torch.float16, 0)], ids=["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K", [(1, 200, 1024), (3, 264, 256), (8, 5000, 4096), (5, 1032, 3072), (2, 16, 15360)])
+def test_gemv_fast_kernel_vs_oracle_and_ideal(pkg, qt, dt, code, M, N, K):
+    """GGUFB200_ALGO_GEMV_FAST never forms W (`fast` contract): within 1e-3 of the reference Linear for
+    fp16 activations, 8e-3 for bf16 -- and at least as close to the fp64 product of the exactly dequantised weight as the
+    reference's own result.  Shapes: partial last row tile, a single super-block, several K-chunks, persistent CTAs."""
+    raw, w = _weight(pkg, qt, N, K, seed=int(qt) + M + N)
+    x = torch.randn(M, K, device=DEV, dtype=dt)
+    bias = torch.randn(N, device=DEV, dtype=torch.float32) * 0.1
+    y = pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_GEMV_FAST)
+    assert torch.equal(y, pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_GEMV_FAST)), "fixed summation order: reproducible"
+    want = oracle.linear(raw, int(qt), N, K, torch_bits(x), code, oracle.DT_F16, torch_bits(bias.to(dt)))
+    ref = torch.from_numpy(bits_to_f32(want.reshape(-1), code).reshape(M, N)).to(DEV)
+    assert rel_fro(y.float().cpu().numpy(), ref.cpu().numpy()) <= (1e-3 if dt == torch.float16 else 8e-3)
+    w32 = pkg.dequant.dequantize_tensor(w, torch.float32, torch.float32)
+    ideal = x.double() @ w32.double().t() + bias.to(dt).double()
+    assert (y.double() - ideal).norm().item() <= 1.02 * (ref.double() - ideal).norm().item()
+    # AUTO takes it exactly when the caller did not ask for a reference-exact weight
+    ya = pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_AUTO)
+    assert torch.equal(ya, y)
+    ye = pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_AUTO | pkg.lib.FLAG_EXACT_W)
+    assert rel_fro(ye.float().cpu().numpy(), ref.cpu().numpy()) <= TOL
+
+
+def test_gemv_fast_kernel_rejects_what_it_cannot_do(pkg):
+    raw, w = _weight(pkg, Q.Q8_0, 64, 512)
+    x = torch.randn(2, 512, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(pkg.lib.GGUFB200Error):
+        pkg.ops.linear_packed(x, w, None, None, pkg.lib.ALGO_GEMV_FAST)               # only Q4_K / Q5_K
+    raw, w = _weight(pkg, Q.Q4_K, 64, 512)
+    with pytest.raises(pkg.lib.GGUFB200Error):
+        pkg.ops.linear_packed(torch.randn(9, 512, device=DEV, dtype=torch.bfloat16), w, None, None, pkg.lib.ALGO_GEMV_FAST)   # M > 8
+    with pytest.raises(pkg.lib.GGUFB200Error):
+        pkg.ops.linear_packed(x, w, None, None, pkg.lib.ALGO_GEMV_FAST | pkg.lib.FLAG_EXACT_W)                                 # contract conflict

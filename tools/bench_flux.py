@@ -63,11 +63,11 @@ class LinearTimer:
         return float(sum(a.elapsed_time(b) for a, b in self.pairs)), len(self.pairs)
 
 
-ROUTE_NAMES = {"fast": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent)",
-               "exact": "reference-exact routes: GEMV / split-K fused / dequant kernel + tcgen05 GEMM"}
+ROUTE_NAMES = {"exact": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent), reference-sequence producers: weight operand bit-identical to the reference's",
+               "fast": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent), fused-multiply-add producers; M <= 8: integer-pattern mma.sync kernel (gemv2)"}
 
 
-def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", numerics="fast",
+def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", numerics="exact",
         block_qtype="Q4_K", batch=1):
     ops_mod, lib = ge._sub("ops"), ge._sub("_lib")
     ops_mod.GGMLOps.Linear.linear_numerics = numerics
@@ -119,7 +119,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--txt", type=int, default=512)
-    ap.add_argument("--numerics", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--numerics", default="exact", choices=["fast", "exact"])
     ap.add_argument("--qtype", default="Q4_K")
     a = ap.parse_args()
     print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype)))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU-side time of the small-M fused Linear (K3): raw C-ABI launches replayed from a CUDA graph (no Python / launch
-overhead in the number), weights rotated through > L2 worth of buffers.  Routes: the TMEM-fed fused kernel (AUTO default,
-32-token items, K ranges across SM pairs) and the reference-exact mma.sync GEMV.  Prints GB/s of packed weight read vs the
+overhead in the number), weights rotated through > L2 worth of buffers.  Routes: the integer-pattern mma.sync kernel (gemv2.cu, `fast` contract), the
+TMEM-fed fused kernel (32-token items, K ranges across SM pairs) and the reference-exact mma.sync GEMV.  Prints GB/s of packed weight read vs the
 measured HBM peak."""
 import json
 import os
@@ -23,7 +23,7 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-ROUTES = (("tmem", lib.ALGO_FUSED_TMEM), ("tmem_spans", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
+ROUTES = (("gemv_fast", lib.ALGO_GEMV_FAST), ("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
 side = torch.cuda.Stream()
 for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
     qt = gguf.GGMLQuantizationType[qname]
@@ -40,6 +40,8 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
             x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             for name, algo in ROUTES:
+                if name == "gemv_fast" and qname not in ("Q4_K", "Q5_K"):
+                    continue
                 need = L.ggufb200_linear_workspace(int(qt), M, N, K, 1, algo)
                 wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
 

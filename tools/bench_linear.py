@@ -102,6 +102,7 @@ def main():
                 "fused": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_MMA | nosplit),
                 "auto": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_AUTO),
                 "auto_exact": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_AUTO | lib.FLAG_EXACT_W),
+                "gemv_fast": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_GEMV_FAST),
                 "gemv": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_GEMV),
                 "dq_mma": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_DEQUANT_MMA),
                 "k1_cublas": lambda: torch.nn.functional.linear(x, dq.dequantize_tensor(nxt(), act)),
