@@ -17,8 +17,8 @@
 // `fast` contract: within 1e-3 of the reference for fp16 activations, 8e-3 for bf16.
 //
 // Data movement: a CTA owns 16 consecutive weight rows, which are CONTIGUOUS in the canonical GGUF layout; their packed bytes
-// are staged K-chunk by K-chunk (12 super-blocks = 3072 k) into a double-buffered shared-memory tile with one bulk async copy
-// (TMA engine, SASS UBLKCP) per row, completion on an mbarrier.  8 warps split a chunk into 24 units of 128 k; their 16 x 8
+// are staged K-chunk by K-chunk (8 super-blocks = 2048 k) into a double-buffered shared-memory tile with one bulk async copy
+// (TMA engine, SASS UBLKCP) per row, completion on an mbarrier.  8 warps split a chunk into 16 units of 128 k; their 16 x 8
 // partial tiles are reduced through shared memory at the end of a row tile.  Persistent grid.
 #include "blocks.cuh"
 
@@ -26,10 +26,10 @@ namespace ggufb200 {
 
 constexpr int kV2Threads = 256;
 constexpr int kV2Warps = 8;
-constexpr int kV2ChunkBlocks = 12;            // super-blocks per staged chunk
+constexpr int kV2ChunkBlocks = 8;             // super-blocks per staged chunk (2048 k): two CTAs per SM fit next to the staged activations at K = 3072
 
 template <int TS> struct V2Cfg {
-    static constexpr int PITCH = kV2ChunkBlocks * TS + 96;          // row pitch of a staged chunk: == 32 (mod 128), so the four rows of a half-warp's 8-byte loads hit disjoint banks
+    static constexpr int PITCH = kV2ChunkBlocks * TS + 96;          // row pitch of a staged chunk: == 96 (mod 128), so the four rows of a half-warp's 8-byte loads hit disjoint banks
     static constexpr int BUF = 16 * PITCH;
 };
 
@@ -88,7 +88,7 @@ __device__ __forceinline__ uint4 v2_lds128(uint32_t a)
 }
 
 // QK = 4: Q4_K (144-byte super-blocks, qs at +16);  QK = 5: Q5_K (176 bytes, qh at +16, qs at +48)
-template <int QK, int ACT>
+template <int QK, int ACT, bool XSM>
 __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__restrict__ W, long long N, long long K, const uint8_t *__restrict__ X,
                                                            long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
                                                            uint8_t *__restrict__ Y, long long ldy)
@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__rest
     float *part = reinterpret_cast<float *>(v2_smem + 64);                   // [8 warps][16][9]
     uint8_t *bufs = v2_smem + 64 + kV2Warps * 16 * 9 * 4 + 64;               // 2 x BUF (16-byte aligned: 64 + 4608 + 64)
     float *xs = reinterpret_cast<float *>(bufs + 2 * Cfg::BUF);              // [K / 32][8]
+    // XSM: the activations themselves are staged once per (persistent) CTA: 8 rows, pitch 2K + 64 bytes (rows of a quarter-warp's
+    // 16-byte loads then fall into disjoint banks).  Every warp re-reads its K range of X for every row tile: from global memory
+    // that is 8 L1 wavefronts per load at M = 8 (8 different rows) and the kernel slows down with M; from shared memory it is 4.
+    uint8_t *xsm = reinterpret_cast<uint8_t *>(xs) + (K / 32) * 8 * 4;
+    const uint32_t xpitch = (uint32_t)(2 * K + 64);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, c = lane & 3;
@@ -121,6 +126,15 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__rest
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         fence_mbar_init();
+    }
+    if constexpr (XSM) {
+        const int per_row = (int)(K / 8);                    // 16-byte vectors per activation row
+        for (int i = tid; i < 8 * per_row; i += kV2Threads) {
+            const int m = i / per_row, v = i - m * per_row;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (m < M) val = *reinterpret_cast<const uint4 *>(X + ((long long)m * ldx + 8ll * v) * 2);
+            *reinterpret_cast<uint4 *>(xsm + (size_t)m * xpitch + 16 * v) = val;
+        }
     }
     // sub-block sums of the activations: xs[sb][m] = sum of X[m, 32 sb .. 32 sb + 31] (fp32, fixed order); rows >= M read as 0
     for (int i = tid; i < (int)(K / 32) * 8; i += kV2Threads) {
@@ -166,6 +180,7 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__rest
     // B-fragment column g = activation row g.  A column of B only feeds the same column of D, so lanes whose row does not
     // exist (g >= M) simply read the last valid row: their results are never stored -- no masking in the inner loop.
     const uint8_t *xrow = X + (long long)(g < M ? g : M - 1) * ldx * 2;
+    const uint32_t xrow_s = smem_u32(xsm) + (uint32_t)g * xpitch;        // XSM: rows >= M were zero-filled
     const uint32_t xs_base = smem_u32(xs) + (uint32_t)(2 * c) * 4;
     const uint32_t quad_base = (uint32_t)(lane & ~3);
 
@@ -217,7 +232,9 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__rest
                     const uint32_t src = quad_base | (uint32_t)s;
                     const float D0 = __shfl_sync(0xffffffffu, Dg, src), E0 = __shfl_sync(0xffffffffu, Eg, src);
                     const float D8 = __shfl_sync(0xffffffffu, Dg8, src), E8 = __shfl_sync(0xffffffffu, Eg8, src);
-                    const uint4 xv = *reinterpret_cast<const uint4 *>(xrow + (kblk + 32 * (4 * h + s) + 8 * c) * 2);
+                    uint4 xv;
+                    if constexpr (XSM) xv = v2_lds128(xrow_s + (uint32_t)((kblk + 32 * (4 * h + s) + 8 * c) * 2));
+                    else xv = *reinterpret_cast<const uint4 *>(xrow + (kblk + 32 * (4 * h + s) + 8 * c) * 2);
                     float d[4];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -290,16 +307,13 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const uint8_t *__rest
     }
 }
 
-template <int QK, int ACT>
-static int gemv2_launch(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype, void *Y,
-                        long long ldy, cudaStream_t st)
+template <int QK, int ACT, bool XSM>
+static int gemv2_launch2(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype, void *Y,
+                         long long ldy, int smem, cudaStream_t st)
 {
-    constexpr int TS = QK == 4 ? 144 : 176;
-    const int smem = 64 + kV2Warps * 16 * 9 * 4 + 64 + 2 * V2Cfg<TS>::BUF + (int)(K / 32) * 8 * 4;
-    if (smem > 227 * 1024) return GGUFB200_E_UNSUPPORTED;
-    auto kern = gemv2_kernel<QK, ACT>;
+    auto kern = gemv2_kernel<QK, ACT, XSM>;
     static unsigned char attr[64] = {};
-    if (!ensure_dynamic_smem(kern, smem, attr)) return GGUFB200_E_CUDA;
+    if (!ensure_dynamic_smem(kern, 227 * 1024, attr)) return GGUFB200_E_CUDA;      // the size depends on K: raise the cap once, to the maximum
     const long long tiles = (N + 15) / 16;
     int per_sm = (227 * 1024) / (smem + 1024);
     if (per_sm > 4) per_sm = 4;
@@ -309,6 +323,19 @@ static int gemv2_launch(const void *W, long long N, long long K, const void *X, 
     kern<<<grid, kV2Threads, smem, st>>>(reinterpret_cast<const uint8_t *>(W), N, K, reinterpret_cast<const uint8_t *>(X), ldx, (int)M, bias, bias_dtype,
                                          reinterpret_cast<uint8_t *>(Y), ldy);
     return cudaGetLastError() == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
+}
+
+template <int QK, int ACT>
+static int gemv2_launch(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype, void *Y,
+                        long long ldy, cudaStream_t st)
+{
+    constexpr int TS = QK == 4 ? 144 : 176;
+    const int base = 64 + kV2Warps * 16 * 9 * 4 + 64 + 2 * V2Cfg<TS>::BUF + (int)(K / 32) * 8 * 4;
+    const long long with_x = base + 8 * (2 * K + 64);
+    if (base > 227 * 1024) return GGUFB200_E_UNSUPPORTED;
+    // stage X when two CTAs per SM still fit (K <= ~3.4 k for Q4_K): beyond that the latency hiding of the second CTA is worth more
+    if (2 * (with_x + 1024) <= 227 * 1024) return gemv2_launch2<QK, ACT, true>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, (int)with_x, st);
+    return gemv2_launch2<QK, ACT, false>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, base, st);
 }
 
 bool gemv2_supported(int type, const void *W, long long N, long long K, long long M)
