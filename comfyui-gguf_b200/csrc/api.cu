@@ -9,6 +9,7 @@
 namespace ggufb200 {
 extern int g_dequant_ctas_per_sm;
 extern int g_dequant_pdl;
+extern int g_gemv2_ctas;
 int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st);
 int unpack_dispatch(int type, const void *packed, long long n_blocks, int16_t *q, int16_t *sc, int16_t *mn, cudaStream_t st);
 int rows_dispatch(int type, const void *packed, long long n_table_rows, long long K, const long long *rows, long long n_rows,
@@ -213,6 +214,10 @@ int ggufb200_set_tuning(int key, int value)
     }
     if (key == 1) {
         g_dequant_pdl = value ? 1 : 0;
+        return GGUFB200_OK;
+    }
+    if (key == 2) {
+        g_gemv2_ctas = value;
         return GGUFB200_OK;
     }
     return GGUFB200_E_UNSUPPORTED;

@@ -68,7 +68,7 @@ ROUTE_NAMES = {"exact": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent), r
 
 
 def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", numerics="exact",
-        block_qtype="Q4_K", batch=1):
+        block_qtype="Q4_K", batch=1, lora_rank=0):
     ops_mod, lib = ge._sub("ops"), ge._sub("_lib")
     ops_mod.GGMLOps.Linear.linear_numerics = numerics
     dev = torch.device(device)
@@ -97,6 +97,34 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
             b.record()
             linear_ms, n_linear = lt.total_ms()
             timed_step_ms = a.elapsed_time(b)
+        lora = None
+        if lora_rank > 0:
+            # a rank-R LoRA patch on every quantised Linear (the patch-list format of ops.py:171-190 / nodes.py:43-47): timed through the same
+            # GGMLOps.Linear forward, in-kernel (one extra k-block of the fused kernel) -- `in_kernel` -- and as two side GEMMs -- `side_gemms`
+            g = torch.Generator().manual_seed(7)
+            n_patched = 0
+            for mod in ours.modules():
+                if isinstance(mod, ops_mod.GGMLOps.Linear) and ops_mod.is_quantized(mod.weight):
+                    N, K = mod.weight.tensor_shape
+                    up = (torch.randn(N, lora_rank, generator=g) * 0.02).to(dev, torch.bfloat16)
+                    down = (torch.randn(lora_rank, K, generator=g) * 0.02).to(dev, torch.bfloat16)
+                    mod.weight.patches = [([(0.8, ("lora", (up, down, float(lora_rank), None, None, None)), 1.0, None, None)], "w")]
+                    n_patched += 1
+            y_l = ours(**inp)
+            ms_in, _ = time_steps(lambda: ours(**inp), steps, warmup)
+            ops_mod.GGMLOps.Linear.lora_in_kernel = False
+            try:
+                y_s = ours(**inp)
+                ms_side, _ = time_steps(lambda: ours(**inp), steps, warmup)
+            finally:
+                ops_mod.GGMLOps.Linear.lora_in_kernel = True
+            lora = {"rank": lora_rank, "patched_linears": n_patched, "ms_per_step_in_kernel": ms_in, "ms_per_step_side_gemms": ms_side,
+                    "in_kernel_over_unpatched": ms_in / ms_ours, "side_gemms_over_unpatched": ms_side / ms_ours,
+                    "output_rel_diff_in_kernel_vs_side_gemms": float(((y_l.float() - y_s.float()).norm() / y_s.float().norm()).item()),
+                    "output_rel_diff_vs_unpatched": float(((y_l.float() - y_ours.float()).norm() / y_ours.float().norm()).item())}
+            for mod in ours.modules():
+                if isinstance(mod, ops_mod.GGMLOps.Linear) and ops_mod.is_quantized(mod.weight):
+                    mod.weight.patches = []
     flops = fh.linear_flops(ours, img_tokens, txt_tokens, batch)
     return {
         "workload": f"Flux.1-dev-shape DiT ({depth} double + {depth_single} single blocks), block Linears {block_qtype}, others BF16, "
@@ -108,7 +136,7 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
         "packed_weight_gb": packed_bytes / 1e9, "output_rel_err_vs_reference_chain": rel, "output_finite": finite,
         "linear_ms": linear_ms, "other_ms": timed_step_ms - linear_ms, "instrumented_step_ms": timed_step_ms, "quantised_linear_calls": n_linear,
         "linear_tflops_rate_inside_linears": flops / (linear_ms * 1e-3) / 1e12,
-        "numerics": numerics, "large_m_route": ROUTE_NAMES[numerics],
+        "numerics": numerics, "large_m_route": ROUTE_NAMES[numerics], "lora": lora,
     }
 
 
@@ -121,5 +149,6 @@ if __name__ == "__main__":
     ap.add_argument("--txt", type=int, default=512)
     ap.add_argument("--numerics", default="exact", choices=["fast", "exact"])
     ap.add_argument("--qtype", default="Q4_K")
+    ap.add_argument("--lora", type=int, default=0, help="also time the step with a rank-R LoRA on every quantised Linear")
     a = ap.parse_args()
-    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype)))
+    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype, lora_rank=a.lora)))

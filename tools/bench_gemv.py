@@ -23,6 +23,10 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
+CTAS = int(os.environ.get("GEMV2_CTAS", "0"))       # A/B of the CTAs-per-SM choice of gemv2 (needs GGUFB200_ALLOW_TUNING=1)
+if CTAS:
+    assert L.ggufb200_set_tuning(2, CTAS) == 0, "set GGUFB200_ALLOW_TUNING=1"
+ONLY = os.environ.get("GEMV_ROUTES", "").split(",") if os.environ.get("GEMV_ROUTES") else None
 ROUTES = (("gemv_fast", lib.ALGO_GEMV_FAST), ("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
 side = torch.cuda.Stream()
 for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
@@ -41,6 +45,8 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             for name, algo in ROUTES:
                 if name == "gemv_fast" and qname not in ("Q4_K", "Q5_K"):
+                    continue
+                if ONLY and name not in ONLY:
                     continue
                 need = L.ggufb200_linear_workspace(int(qt), M, N, K, 1, algo)
                 wsb = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
