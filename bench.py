@@ -275,8 +275,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning knob: dequant CTAs per SM (0 = library default)")
     ap.add_argument("--no-pdl", action="store_true", help="tuning knob: disable programmatic dependent launch")
+    ap.add_argument("--no-src-stable", action="store_true", help="A/B: launch the dequant kernel without GGUFB200_DEQUANT_SRC_STABLE")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of replaying each step from a CUDA graph")
     ap.add_argument("--sweep-detail", action="store_true", help="also print per-(qtype,shape) GB/s lines to stderr")
     ap.add_argument("--no-flux", action="store_true", help="skip the secondary metric (Flux.1-shape Q4_K denoise step A/B)")
@@ -291,12 +291,10 @@ def main():
     import __graft_entry__ as ge
     import oracle  # only for the seeded synthetic block generator and the cpu_baseline leg
 
-    if args.ctas_per_sm or args.no_pdl:
+    if args.no_pdl:
         os.environ["GGUFB200_ALLOW_TUNING"] = "1"      # benchmark-only launch knobs of the dequant kernel (never routing)
     dq, ops, rep = ge._sub("dequant"), ge._sub("ops"), ge._sub("replicas")
     lib = ge._sub("_lib").lib()        # raises if the CUDA extension is missing: no fallback
-    if args.ctas_per_sm and lib.ggufb200_set_tuning(0, args.ctas_per_sm) != 0:
-        raise RuntimeError("tuning refused")
     if args.no_pdl and lib.ggufb200_set_tuning(1, 0) != 0:
         raise RuntimeError("tuning refused")
     rank, local_rank, world = rep.init()
@@ -330,8 +328,12 @@ def main():
             step_elems += N * K
     stream = torch.cuda.current_stream(dev)
 
+    # math code 0 = fp16 (the reference default).  The packed tensors are constant weights, resident since set-up, so the call
+    # carries the same GGUFB200_DEQUANT_SRC_STABLE promise the package's dequantize() / dequantize_tensor() make by default.
+    math_arg = 0 if args.no_src_stable else ge._sub("_lib").DEQUANT_SRC_STABLE
+
     def launch(t):
-        rc = lib.ggufb200_dequant(int(t["qt"]), t["w"].data_ptr(), t["n_blocks"], t["out"].data_ptr(), 0, 0, stream.cuda_stream)
+        rc = lib.ggufb200_dequant(int(t["qt"]), t["w"].data_ptr(), t["n_blocks"], t["out"].data_ptr(), 0, math_arg, stream.cuda_stream)
         if rc != 0:
             raise RuntimeError(f"ggufb200_dequant rc={rc}")
 
@@ -548,6 +550,7 @@ def main():
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD, "tensors_per_step": n_tensors, "elements_per_step": step_elems,
                        "algorithmic_bytes_per_step": step_bytes, "parallelism": f"{world} independent replica(s), no collective",
+                       "launch": "ggufb200_dequant(..., math_dtype = fp16" + ("" if args.no_src_stable else " | GGUFB200_DEQUANT_SRC_STABLE") + ")",
                        "l2": "inputs larger than L2: 1.05 GB of distinct packed tensors + 2.83 GB of distinct outputs per step vs 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "flux_step": flux,
             "numa": numa,

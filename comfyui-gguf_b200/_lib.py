@@ -18,6 +18,8 @@ ALGO_AUTO, ALGO_GEMV, ALGO_FUSED_MMA, ALGO_DEQUANT_MMA, ALGO_FUSED_TMEM, ALGO_GE
 ALGO_MASK = 0xFF
 # per-call switches OR-ed into `algo` (include/ggufb200.h)
 FLAG_EXACT_W, FLAG_GENERIC, FLAG_TILE384, FLAG_NOSPLIT, FLAG_UNSTAGED, FLAG_TILE192 = 0x100, 0x200, 0x400, 0x800, 0x1000, 0x2000
+FLAG_W_STABLE = 0x4000          # ggufb200_linear: no kernel still in flight writes the packed weight (prefetch under the previous kernel's tail)
+DEQUANT_SRC_STABLE = 0x100      # same promise for ggufb200_dequant, OR-ed into math_dtype
 OP_DEQUANT, OP_LINEAR, OP_ROWS, OP_LINEAR_MMA = 0, 1, 2, 3
 
 

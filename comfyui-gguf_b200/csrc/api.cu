@@ -7,10 +7,9 @@
 #include "blocks.cuh"
 
 namespace ggufb200 {
-extern int g_dequant_ctas_per_sm;
 extern int g_dequant_pdl;
 extern int g_gemv2_ctas;
-int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st);
+int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st, bool stable = false);
 int unpack_dispatch(int type, const void *packed, long long n_blocks, int16_t *q, int16_t *sc, int16_t *mn, cudaStream_t st);
 int rows_dispatch(int type, const void *packed, long long n_table_rows, long long K, const long long *rows, long long n_rows,
                   void *out, int out_dtype, int math_dtype, cudaStream_t st);
@@ -32,7 +31,7 @@ void gemm4_plan_info(long long M, long long N, long long K, size_t ws_bytes, int
 int gemv_max_m();
 bool gemv2_supported(int type, const void *W, long long N, long long K, long long M);
 int gemv2_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype, const void *bias,
-                   int bias_dtype, void *Y, long long ldy, cudaStream_t st);
+                   int bias_dtype, void *Y, long long ldy, cudaStream_t st, bool w_stable = false);
 size_t repack_bytes(int type, long long N, long long K, int *pitch, long long *span_stride);
 int repack_dispatch(int type, const void *W, long long N, long long K, void *out, cudaStream_t st);
 }  // namespace ggufb200
@@ -208,10 +207,6 @@ int ggufb200_set_tuning(int key, int value)
         return e && e[0] == '1';
     }();
     if (!allowed) return GGUFB200_E_UNSUPPORTED;
-    if (key == 0) {
-        g_dequant_ctas_per_sm = value;
-        return GGUFB200_OK;
-    }
     if (key == 1) {
         g_dequant_pdl = value ? 1 : 0;
         return GGUFB200_OK;
@@ -226,13 +221,15 @@ int ggufb200_set_tuning(int key, int value)
 int ggufb200_dequant(int ggml_type, const void *packed, int64_t n_blocks, void *out, int out_dtype, int math_dtype, void *stream)
 {
     if (!type_geom(ggml_type, nullptr, nullptr)) return GGUFB200_E_TYPE;
+    const bool stable = (math_dtype & GGUFB200_DEQUANT_SRC_STABLE) != 0;
+    math_dtype &= ~GGUFB200_DEQUANT_SRC_STABLE;
     if (!dtype_ok(out_dtype) || !dtype_ok(math_dtype)) return GGUFB200_E_DTYPE;
     if (n_blocks < 0) return GGUFB200_E_SHAPE;
     if (n_blocks == 0) return GGUFB200_OK;
     if (!packed || !out) return GGUFB200_E_NULL;
     if (!aligned16(out)) return GGUFB200_E_ALIGN;
     if (int rc = device_check()) return rc;
-    return dequant_dispatch(ggml_type, packed, n_blocks, out, out_dtype, math_dtype, (cudaStream_t)stream);
+    return dequant_dispatch(ggml_type, packed, n_blocks, out, out_dtype, math_dtype, (cudaStream_t)stream, stable);
 }
 
 int ggufb200_unpack_int(int ggml_type, const void *packed, int64_t n_blocks, int16_t *q, int16_t *sc, int16_t *mn, void *stream)
@@ -319,7 +316,7 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
         return gemv_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, math_dtype, bias, bias_dtype, Y, ldy, st);
     case GGUFB200_ALGO_GEMV_FAST:
         if (math_dtype != kF16 || (flags & GGUFB200_FLAG_EXACT_W)) return GGUFB200_E_UNSUPPORTED;
-        return gemv2_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
+        return gemv2_dispatch(ggml_type, W_packed, N, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st, (flags & GGUFB200_FLAG_W_STABLE) != 0);
     case GGUFB200_ALGO_FUSED_MMA: {
         if (!fused_type(ggml_type)) return GGUFB200_E_UNSUPPORTED;
         int f = 0;
@@ -337,7 +334,7 @@ static int linear_impl(int ggml_type, const void *W_packed, const void *W_spans,
     }
     case GGUFB200_ALGO_DEQUANT_MMA: {
         if (ws_avail < dense) return GGUFB200_E_WORKSPACE;
-        int rc = dequant_dispatch(ggml_type, W_packed, N * (K / bs), workspace, act_dtype, math_dtype, st);
+        int rc = dequant_dispatch(ggml_type, W_packed, N * (K / bs), workspace, act_dtype, math_dtype, st, (flags & GGUFB200_FLAG_W_STABLE) != 0);
         if (rc != GGUFB200_OK) return rc;
         return gemm3_dense_dispatch(workspace, N, K, K, X, M, ldx, act_dtype, bias, bias_dtype, Y, ldy, st);
     }

@@ -6,20 +6,22 @@
 // Data movement (algorithmic bytes per element = TS/BS read + sizeof(out) written):
 //   * the packed block stream is treated as a flat byte stream (block sizes 18/22/34/84/110/
 //     210 B are not 16 B multiples, so 2-D tensor maps are illegal for most shapes); it is cut
-//     into tiles of TILE_ELEMS elements whose byte span is always a multiple of 16 B
-//   * each tile is staged into shared memory by ONE elected thread with the TMA engine
-//     (cp.async.bulk, SASS UBLKCP) into a STAGES-deep ring, completion on an mbarrier;
-//     the ring is refilled as soon as a slot has been consumed
-//   * every thread unpacks runs of 4/8 consecutive elements from shared memory (blocks.cuh)
-//     and writes one 16-byte vector per run, so a warp stores 512 contiguous bytes
-//   * persistent grid: gridDim = min(tiles, SMs * CTAs/SM), tile = blockIdx + i * gridDim
+//     into tiles of 4096 elements whose byte span is always a multiple of 16 B
+//   * ONE TILE PER CTA (128 threads), CTAs handed out by the hardware in address order: the write front stays
+//     compact, an SM that happens to be slower simply takes fewer tiles, and 16 CTAs per SM cover each other's load
+//     latency.  (Round 1's persistent CTAs with a 3-stage prefetch ring and strided tiles: 0.885 of the measured copy peak
+//     on the Flux-shape sweep, 5.8 TB/s on a 1 GB output; this form: 0.949 and 6.75 TB/s --
+//     profiles/r02_k1_variants_ab.log, same effect as in tools/probe_write.cu's plain-store probes.)
+//   * the tile is staged into shared memory by thread 0 with the TMA engine (cp.async.bulk, SASS UBLKCP), completion on
+//     an mbarrier that only thread 0 polls; the other threads sleep in the CTA barrier
+//   * every thread unpacks one run of 32 consecutive elements from shared memory (blocks.cuh) into a linear output
+//     tile in shared memory, which leaves through ONE bulk async store: every HBM write is a full line
 #include "blocks.cuh"
 
 namespace ggufb200 {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;       // threads per CTA of the dequant kernel = 4096-element tiles (256: 0.929, 64: 0.80 of the copy peak on the Flux-shape sweep)
 
-int g_dequant_ctas_per_sm = 0;  // 0 = default; set through ggufb200_set_tuning(0, v)
 int g_dequant_pdl = 1;          // programmatic dependent launch of the dequant kernel; ggufb200_set_tuning(1, 0/1)
 
 // bulk async copy shared -> global (TMA engine), tracked with bulk async-groups
@@ -31,129 +33,102 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 __device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// One thread = one run of 32 consecutive elements (a whole 32-block, or one/two scale groups of a K-quant
-// super-block): the header is decoded once per 32 elements.  The 32 results (64 B fp16/bf16, 128 B fp32) go to a
-// linear output tile in shared memory in 16-byte chunks -- chunk order rotated per lane so the STS.128 are bank
-// conflict free -- and the finished tile leaves through ONE bulk async store (TMA engine), so the threads never
-// compute a global address and every HBM write is a full line.
-template <class Q, int MATH, int OUT, int STAGES, int TILE_ELEMS>
-__global__ void __launch_bounds__(kThreads) dequant_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst, long long n_blocks,
-                                                           int bulk_ok)
+// One thread = one run of 32 consecutive elements of the tile at `tile` (shared memory); results to the linear output tile.
+template <class Q, int MATH, int OUT>
+__device__ __forceinline__ void dequant_tile(const uint8_t *tile, uint8_t *otile, int tile_elems, int tid, int lane)
 {
     constexpr int OB = OutT<OUT>::bytes;
     constexpr int EPC = 16 / OB;                           // elements per 16-byte chunk: 8 or 4
     constexpr int CH = 32 / EPC;                           // chunks per thread: 4 or 8
-    constexpr int TILE_BLOCKS = TILE_ELEMS / Q::BS;
-    constexpr int TILE_BYTES = TILE_BLOCKS * Q::TS;
-    constexpr int SLOT_BYTES = TILE_BYTES + 16;            // +16: tail over-read rounding
-    constexpr int OUT_BYTES = TILE_ELEMS * OB;
     constexpr int GROUP = GroupOf<Q>::value;
-    static_assert(TILE_BYTES % 16 == 0, "tile byte span must be a multiple of 16");
-    static_assert(TILE_ELEMS == kThreads * 32 && TILE_ELEMS % Q::BS == 0, "tile shape");
-
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);   // STAGES mbarriers
-    uint8_t *slots = smem + 128;
-    uint8_t *outs = slots + STAGES * SLOT_BYTES;           // two output tiles
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    const long long total_bytes = n_blocks * (long long)Q::TS;
-    const long long n_elems = n_blocks * (long long)Q::BS;
-
-    // Programmatic dependent launch: let the next kernel in the stream be scheduled while this one drains, and
-    // do this kernel's own set-up before waiting for the previous kernel's memory to be complete and visible.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    // bytes of tile t (the last tile may be short); bulk copies are rounded up to 16 B, which
-    // stays inside the 16-byte granule that holds the last valid byte
-    auto issue = [&](long long t, int slot) {
-        long long off = t * (long long)TILE_BYTES;
-        long long len = total_bytes - off;
-        if (len > TILE_BYTES) len = TILE_BYTES;
-        uint32_t bytes = (uint32_t)((len + 15) & ~15LL);
-        mbar_arrive_expect_tx(&full[slot], bytes);
-        bulk_g2s(slots + slot * SLOT_BYTES, src + off, bytes, &full[slot]);
-    };
-
-    if (bulk_ok && tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-            long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (t < n_tiles) issue(t, s);
-        }
-    }
-
-    // this thread's run inside any tile
     const int blk_in_tile = (tid * 32) / Q::BS;
     const int e0 = (tid * 32) % Q::BS;
     const int rot = (CH == 4) ? (lane >> 1) : lane;
-
-    int it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-        const int slot = it % STAGES;
-        const uint8_t *tile = slots + slot * SLOT_BYTES;
-        uint8_t *otile = outs + (it & 1) * OUT_BYTES;
-        if (bulk_ok) {
-            mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
-        } else {
-            // unaligned source pointer (never produced by torch allocations): cooperative byte copy
-            long long off = t * (long long)TILE_BYTES;
-            long long len = total_bytes - off;
-            if (len > TILE_BYTES) len = TILE_BYTES;
-            for (int i = tid; i < (int)len; i += kThreads) slots[slot * SLOT_BYTES + i] = src[off + i];
-            __syncthreads();
-        }
-
-        const long long elem_base = t * (long long)TILE_ELEMS;
-        const long long left = n_elems - elem_base;
-        const int tile_elems = left < TILE_ELEMS ? (int)left : TILE_ELEMS;   // a multiple of 32
-        if (tid * 32 < tile_elems) {
-            const uint8_t *blk = tile + blk_in_tile * Q::TS;
-            const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
-            GroupScale<MATH> g1 = g0;
-            if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
-            const uint32_t obase = smem_u32(otile) + tid * (32 * OB);
+    if (tid * 32 < tile_elems) {
+        const uint8_t *blk = tile + blk_in_tile * Q::TS;
+        const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
+        GroupScale<MATH> g1 = g0;
+        if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
+        const uint32_t obase = smem_u32(otile) + tid * (32 * OB);
 #pragma unroll
-            for (int p = 0; p < CH; ++p) {
-                const int c = (p + rot) & (CH - 1);          // rotated chunk order: conflict-free STS.128
-                const int e = e0 + c * EPC;
-                const bool second = (GROUP == 16) && (c * EPC >= 16);
-                GroupScale<MATH> g;
-                g.a = second ? g1.a : g0.a;
-                g.b = second ? g1.b : g0.b;
-                typename Math<MATH>::T2 v[EPC / 2];
-                dequant_elems<Q, MATH, EPC>(blk, e, g, v);
-                if constexpr (OUT == kF32) {
-                    float2 f0 = Math<MATH>::to_f32x2(v[0]), f1 = Math<MATH>::to_f32x2(v[1]);
-                    st_shared_v4(obase + c * 16, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
-                } else {
-                    st_shared_v4(obase + c * 16, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]),
-                                 pack16<OUT, MATH>(v[3]));
-                }
+        for (int p = 0; p < CH; ++p) {
+            const int c = (p + rot) & (CH - 1);          // rotated chunk order: conflict-free STS.128
+            const int e = e0 + c * EPC;
+            const bool second = (GROUP == 16) && (c * EPC >= 16);
+            GroupScale<MATH> g;
+            g.a = second ? g1.a : g0.a;
+            g.b = second ? g1.b : g0.b;
+            typename Math<MATH>::T2 v[EPC / 2];
+            dequant_elems<Q, MATH, EPC>(blk, e, g, v);
+            if constexpr (OUT == kF32) {
+                float2 f0 = Math<MATH>::to_f32x2(v[0]), f1 = Math<MATH>::to_f32x2(v[1]);
+                st_shared_v4(obase + c * 16, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
+            } else {
+                st_shared_v4(obase + c * 16, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]),
+                             pack16<OUT, MATH>(v[3]));
             }
         }
-        fence_proxy_async_smem();   // output tile written through the generic proxy, read by the TMA engine
-        __syncthreads();            // tile complete; every thread is also done reading the input slot
-        if (tid == 0) {
-            bulk_s2g(reinterpret_cast<uint8_t *>(dst) + elem_base * OB, otile, (uint32_t)(tile_elems * OB));
-            if (bulk_ok) {
-                long long tn = t + (long long)STAGES * gridDim.x;
-                if (tn < n_tiles) issue(tn, slot);
-            }
-            bulk_wait_read_le1();   // the other output buffer (stored one tile ago) has been read out
-        }
-        __syncthreads();
     }
-    if (tid == 0) bulk_wait_all();
+}
+
+// One tile per CTA (see the file header).  flags: bit 0 = the packed pointer is 16-byte aligned (bulk copy legal),
+// bit 1 = GGUFB200_DEQUANT_SRC_STABLE.
+template <class Q, int MATH, int OUT, int THREADS>
+__global__ void __launch_bounds__(THREADS) dequant_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst, long long n_blocks,
+                                                              int flags)
+{
+    constexpr int OB = OutT<OUT>::bytes;
+    constexpr int TILE_ELEMS = THREADS * 32;
+    constexpr int TILE_BLOCKS = TILE_ELEMS / Q::BS;
+    constexpr int TILE_BYTES = TILE_BLOCKS * Q::TS;
+    static_assert(TILE_BYTES % 16 == 0, "tile byte span must be a multiple of 16");
+    static_assert(TILE_ELEMS % Q::BS == 0, "tile shape");
+    const int bulk_ok = flags & 1;
+    const bool early = bulk_ok && (flags & 2);
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *tile = smem + 128;
+    uint8_t *otile = tile + TILE_BYTES + 16 + ((128 - ((TILE_BYTES + 16) & 127)) & 127);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const long long t = blockIdx.x;
+    const long long total_bytes = n_blocks * (long long)Q::TS;
+    const long long n_elems = n_blocks * (long long)Q::BS;
+    long long off = t * (long long)TILE_BYTES;
+    long long len = total_bytes - off;
+    if (len > TILE_BYTES) len = TILE_BYTES;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (bulk_ok) {
+        // Only thread 0 touches the mbarrier (init, copy, wait); the other 255 threads sleep in the CTA barrier instead of
+        // polling, so the warps of the SM's other CTAs that are unpacking get the issue slots.
+        if (tid == 0) {
+            mbar_init(full, 1);
+            fence_mbar_init();
+            if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
+            uint32_t bytes = (uint32_t)((len + 15) & ~15LL);
+            mbar_arrive_expect_tx(full, bytes);
+            bulk_g2s(tile, src + off, bytes, full);
+            mbar_wait(full, 0);
+        }
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (int i = tid; i < (int)len; i += THREADS) tile[i] = src[off + i];
+    }
+    __syncthreads();
+    const long long elem_base = t * (long long)TILE_ELEMS;
+    const long long left = n_elems - elem_base;
+    const int tile_elems = left < TILE_ELEMS ? (int)left : TILE_ELEMS;
+    dequant_tile<Q, MATH, OUT>(tile, otile, tile_elems, tid, lane);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        if (early) asm volatile("griddepcontrol.wait;" ::: "memory");
+        bulk_s2g(reinterpret_cast<uint8_t *>(dst) + elem_base * OB, otile, (uint32_t)(tile_elems * OB));
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the shared-memory tile must outlive the engine's read of it
+    }
 }
 
 // BF16 "quantised" type (dequant.py:61-62): widen to fp32, then cast to the output dtype
@@ -214,33 +189,22 @@ __global__ void unpack_int_kernel(const uint8_t *__restrict__ src, long long n_b
 }
 
 // ------------------------------------------------------------------ host-side dispatch
-template <class Q, int MATH, int OUT> static int launch_dequant(const void *packed, long long n_blocks, void *out, cudaStream_t st)
+template <class Q, int MATH, int OUT> static int launch_dequant(const void *packed, long long n_blocks, void *out, bool src_stable, cudaStream_t st)
 {
-    constexpr int STAGES = 3;
-    constexpr int TILE_ELEMS = kThreads * 32;
-    constexpr int TILE_BLOCKS = TILE_ELEMS / Q::BS;
-    constexpr int SLOT_BYTES = TILE_BLOCKS * Q::TS + 16;
-    constexpr int SMEM = 128 + STAGES * SLOT_BYTES + 2 * TILE_ELEMS * OutT<OUT>::bytes;
-    auto kern = dequant_kernel<Q, MATH, OUT, STAGES, TILE_ELEMS>;
+    constexpr int THREADS = kThreads;
+    constexpr int TILE_BLOCKS = THREADS * 32 / Q::BS;
+    constexpr int TB = TILE_BLOCKS * Q::TS + 16;
+    constexpr int SMEM = 128 + TB + ((128 - (TB & 127)) & 127) + THREADS * 32 * OutT<OUT>::bytes;
+    auto kern = dequant_kernel<Q, MATH, OUT, THREADS>;
     static unsigned char smem_set[64] = {};
-    static int resident_on[64] = {};   // CTAs of this instantiation that fit on one SM, per device
     if (!ensure_dynamic_smem(kern, SMEM, smem_set)) return GGUFB200_E_CUDA;
-    int &resident = resident_on[device_slot()];
-    if (resident == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, SMEM) != cudaSuccess || n < 1) n = 1;
-        resident = n > 4 ? 4 : n;
-    }
-    long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    int per_sm = g_dequant_ctas_per_sm > 0 ? g_dequant_ctas_per_sm : resident;
-    if (per_sm > resident) per_sm = resident;
-    long long cap = (long long)sm_count() * per_sm;
-    long long rounds = (n_tiles + cap - 1) / cap;            // every CTA gets the same number of tiles (+-1)
-    long long grid = (n_tiles + rounds - 1) / rounds;
-    int bulk_ok = ((reinterpret_cast<uintptr_t>(packed) & 15) == 0) ? 1 : 0;
+    const long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    if (n_tiles > 0x7fffffffll) return GGUFB200_E_SHAPE;
+    int flags = ((reinterpret_cast<uintptr_t>(packed) & 15) == 0) ? 1 : 0;
+    if (src_stable) flags |= 2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.gridDim = dim3((unsigned)n_tiles);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -248,46 +212,46 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_dequant_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const uint8_t *>(packed), out, (long long)n_blocks, bulk_ok);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const uint8_t *>(packed), out, (long long)n_blocks, flags);
     return e == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 
-template <class Q, int MATH> static int dispatch_out(const void *packed, long long n_blocks, void *out, int out_dtype, cudaStream_t st)
+template <class Q, int MATH> static int dispatch_out(const void *packed, long long n_blocks, void *out, int out_dtype, bool stable, cudaStream_t st)
 {
     switch (out_dtype) {
-    case kF16: return launch_dequant<Q, MATH, kF16>(packed, n_blocks, out, st);
-    case kBF16: return launch_dequant<Q, MATH, kBF16>(packed, n_blocks, out, st);
-    case kF32: return launch_dequant<Q, MATH, kF32>(packed, n_blocks, out, st);
+    case kF16: return launch_dequant<Q, MATH, kF16>(packed, n_blocks, out, stable, st);
+    case kBF16: return launch_dequant<Q, MATH, kBF16>(packed, n_blocks, out, stable, st);
+    case kF32: return launch_dequant<Q, MATH, kF32>(packed, n_blocks, out, stable, st);
     }
     return GGUFB200_E_DTYPE;
 }
 
-template <class Q> static int dispatch_math(const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st)
+template <class Q> static int dispatch_math(const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, bool stable, cudaStream_t st)
 {
     switch (math_dtype) {
-    case kF16: return dispatch_out<Q, kF16>(packed, n_blocks, out, out_dtype, st);
-    case kBF16: return dispatch_out<Q, kBF16>(packed, n_blocks, out, out_dtype, st);
-    case kF32: return dispatch_out<Q, kF32>(packed, n_blocks, out, out_dtype, st);
+    case kF16: return dispatch_out<Q, kF16>(packed, n_blocks, out, out_dtype, stable, st);
+    case kBF16: return dispatch_out<Q, kBF16>(packed, n_blocks, out, out_dtype, stable, st);
+    case kF32: return dispatch_out<Q, kF32>(packed, n_blocks, out, out_dtype, stable, st);
     }
     return GGUFB200_E_DTYPE;
 }
 
-int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st)
+int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out, int out_dtype, int math_dtype, cudaStream_t st, bool stable)
 {
     if (n_blocks == 0) return GGUFB200_OK;
     switch (type) {
-    case T_Q4_0: return dispatch_math<Block<T_Q4_0>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q4_1: return dispatch_math<Block<T_Q4_1>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q5_0: return dispatch_math<Block<T_Q5_0>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q5_1: return dispatch_math<Block<T_Q5_1>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q8_0: return dispatch_math<Block<T_Q8_0>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q2_K: return dispatch_math<Block<T_Q2_K>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q3_K: return dispatch_math<Block<T_Q3_K>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q4_K: return dispatch_math<Block<T_Q4_K>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q5_K: return dispatch_math<Block<T_Q5_K>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_Q6_K: return dispatch_math<Block<T_Q6_K>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_IQ4_NL: return dispatch_math<Block<T_IQ4_NL>>(packed, n_blocks, out, out_dtype, math_dtype, st);
-    case T_IQ4_XS: return dispatch_math<Block<T_IQ4_XS>>(packed, n_blocks, out, out_dtype, math_dtype, st);
+    case T_Q4_0: return dispatch_math<Block<T_Q4_0>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q4_1: return dispatch_math<Block<T_Q4_1>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q5_0: return dispatch_math<Block<T_Q5_0>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q5_1: return dispatch_math<Block<T_Q5_1>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q8_0: return dispatch_math<Block<T_Q8_0>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q2_K: return dispatch_math<Block<T_Q2_K>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q3_K: return dispatch_math<Block<T_Q3_K>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q4_K: return dispatch_math<Block<T_Q4_K>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q5_K: return dispatch_math<Block<T_Q5_K>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_Q6_K: return dispatch_math<Block<T_Q6_K>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_IQ4_NL: return dispatch_math<Block<T_IQ4_NL>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
+    case T_IQ4_XS: return dispatch_math<Block<T_IQ4_XS>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
     case T_BF16: {
         long long blocks = (n_blocks + (long long)kThreads * 8 - 1) / ((long long)kThreads * 8);
         long long cap = (long long)sm_count() * 8;

@@ -108,7 +108,7 @@ __device__ __forceinline__ uint4 v2_lds128(uint32_t a)
 template <int QK, int ACT, bool XSM>
 __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const __grid_constant__ CUtensorMap tmW, long long N, long long K, const uint8_t *__restrict__ X,
                                                            long long ldx, int M, const void *__restrict__ bias, int bias_dtype,
-                                                           uint8_t *__restrict__ Y, long long ldy, int NS)
+                                                           uint8_t *__restrict__ Y, long long ldy, int NS, int w_stable)
 {
     constexpr int TS = QK == 4 ? 144 : 176;
     constexpr int QS_OFF = QK == 4 ? 16 : 48;
@@ -150,9 +150,16 @@ __global__ void __launch_bounds__(kV2Threads) gemv2_kernel(const __grid_constant
     if (warp == kV2Warps && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     __syncthreads();
     // Programmatic dependent launch: the set-up above overlaps the tail of the previous kernel in the stream; nothing below may
-    // touch global memory before that kernel's writes are visible (the weight may have been written by it, too).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // touch global memory before that kernel's writes are visible.  W_STABLE (the caller's promise that no kernel still in
+    // flight writes the packed weight): the producer starts filling the ring at once -- the whole ring is in flight while the
+    // previous kernel drains -- and only the consumers (activations, bias, Y) wait.
+    if (w_stable) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (warp != kV2Warps) asm volatile("griddepcontrol.wait;" ::: "memory");
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
 
     if (warp == kV2Warps) {
         // ===================== producer: one tensor-map copy per (row tile, K chunk) stage
@@ -363,7 +370,7 @@ template <int TS> static bool v2_make_map(CUtensorMap *tm, const void *W, long l
 
 template <int QK, int ACT, bool XSM>
 static int gemv2_launch2(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype, void *Y,
-                         long long ldy, int ns, int ctas, int smem, cudaStream_t st)
+                         long long ldy, int ns, int ctas, int smem, int w_stable, cudaStream_t st)
 {
     constexpr int TS = QK == 4 ? 144 : 176;
     auto kern = gemv2_kernel<QK, ACT, XSM>;
@@ -384,7 +391,7 @@ static int gemv2_launch2(const void *W, long long N, long long K, const void *X,
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, tmW, N, K, reinterpret_cast<const uint8_t *>(X), ldx, (int)M, bias, bias_dtype, reinterpret_cast<uint8_t *>(Y), ldy,
-                              ns) == cudaSuccess
+                              ns, w_stable) == cudaSuccess
                ? GGUFB200_OK
                : GGUFB200_E_CUDA;
 }
@@ -425,13 +432,13 @@ template <int TS> static V2Plan v2_plan(long long N, long long K, long long M)
 
 template <int QK, int ACT>
 static int gemv2_launch(const void *W, long long N, long long K, const void *X, long long M, long long ldx, const void *bias, int bias_dtype, void *Y,
-                        long long ldy, cudaStream_t st)
+                        long long ldy, int w_stable, cudaStream_t st)
 {
     constexpr int TS = QK == 4 ? 144 : 176;
     const V2Plan p = v2_plan<TS>(N, K, M);
     if (!p.ok) return GGUFB200_E_UNSUPPORTED;
-    if (p.xsm) return gemv2_launch2<QK, ACT, true>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, p.ns, p.ctas, p.smem, st);
-    return gemv2_launch2<QK, ACT, false>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, p.ns, p.ctas, p.smem, st);
+    if (p.xsm) return gemv2_launch2<QK, ACT, true>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, p.ns, p.ctas, p.smem, w_stable, st);
+    return gemv2_launch2<QK, ACT, false>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, p.ns, p.ctas, p.smem, w_stable, st);
 }
 
 bool gemv2_supported(int type, const void *W, long long N, long long K, long long M)
@@ -443,14 +450,15 @@ bool gemv2_supported(int type, const void *W, long long N, long long K, long lon
 }
 
 int gemv2_dispatch(int type, const void *W, long long N, long long K, const void *X, long long M, long long ldx, int act_dtype, const void *bias,
-                   int bias_dtype, void *Y, long long ldy, cudaStream_t st)
+                   int bias_dtype, void *Y, long long ldy, cudaStream_t st, bool w_stable)
 {
+    const int ws = w_stable ? 1 : 0;
     if (!gemv2_supported(type, W, N, K, M)) return GGUFB200_E_UNSUPPORTED;
     if (type == T_Q4_K)
-        return act_dtype == kBF16 ? gemv2_launch<4, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st)
-                                  : gemv2_launch<4, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
-    return act_dtype == kBF16 ? gemv2_launch<5, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st)
-                              : gemv2_launch<5, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, st);
+        return act_dtype == kBF16 ? gemv2_launch<4, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, st)
+                                  : gemv2_launch<4, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, st);
+    return act_dtype == kBF16 ? gemv2_launch<5, kBF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, st)
+                              : gemv2_launch<5, kF16>(W, N, K, X, M, ldx, bias, bias_dtype, Y, ldy, ws, st);
 }
 
 }  // namespace ggufb200

@@ -69,7 +69,13 @@ def _as_bytes(data: torch.Tensor) -> torch.Tensor:
     return raw.contiguous()
 
 
-def dequantize(data, qtype, oshape, dtype=None, out_dtype=None):
+# The packed bytes handed to dequantize() are produced by loads, host-to-device copies or ordinary torch kernels, none of which
+# signals programmatic launch completion before its last write -- so they are complete before our kernel starts and the
+# GGUFB200_DEQUANT_SRC_STABLE promise (include/ggufb200.h) holds by construction.  Set to False to launch without it.
+SRC_STABLE = True
+
+
+def dequantize(data, qtype, oshape, dtype=None, out_dtype=None, src_stable=None):
     """dequant.py:30-44.  `dtype` is the MATH dtype (None = fp16); the result is in `out_dtype`
     (default: the math dtype, as in the reference where the block functions return it).
     BF16 always yields fp32 in the reference (dequant.py:61-62) unless out_dtype says otherwise."""
@@ -78,6 +84,8 @@ def dequantize(data, qtype, oshape, dtype=None, out_dtype=None):
         raise NotImplementedError(f"ggufb200: no kernel for qtype {getattr(qtype, 'name', qtype)!r} (and no CPU fallback)")
     block_size, type_size = gguf.GGML_QUANT_SIZES[qtype]
     math = _lib.F16 if dtype is None else dtype_code(dtype)
+    if SRC_STABLE if src_stable is None else src_stable:
+        math |= _lib.DEQUANT_SRC_STABLE
     if out_dtype is None:
         out_dtype = torch.float32 if qtype == _Q.BF16 else (torch.float16 if dtype is None else dtype)
     raw = _as_bytes(data)

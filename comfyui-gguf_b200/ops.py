@@ -495,7 +495,8 @@ class GGMLOps(comfy_ops.manual_cast):
                 elif M <= GEMV_MAX_M or N % 8 == 0:                    # (the M <= 8 kernel stores per element: any N)
                     math = math_code(self.dequant_dtype, input.dtype)
                     algo, spans = _lib.ALGO_AUTO, None
-                    exact = _lib.FLAG_EXACT_W if self.linear_numerics != "fast" else 0
+                    # W_STABLE: the packed weight is a parameter (or its host-to-device copy just above): never written by a kernel in flight
+                    exact = (_lib.FLAG_EXACT_W if self.linear_numerics != "fast" else 0) | _lib.FLAG_W_STABLE
                     algo |= exact
                     if (self.repack_spans and resident and math == _F16_CODE and N % 8 == 0 and qtype != _Q.BF16
                             and needs_span_layout(qtype, K) and (M > GEMV_MAX_M or N * K >= (40 << 20))):

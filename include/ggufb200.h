@@ -87,6 +87,14 @@ extern "C" {
 #define GGUFB200_FLAG_NOSPLIT 0x800
 #define GGUFB200_FLAG_UNSTAGED 0x1000
 #define GGUFB200_FLAG_TILE192 0x2000 /* FUSED_TMEM: force 192-token items (double-buffered accumulators); default: cost model */
+/*   W_STABLE   the caller promises that no kernel still in flight on `stream` writes W_packed (model weights: written once at
+ *              load time).  The kernels are launched with programmatic stream serialization; with the promise GEMV_FAST starts
+ *              streaming the packed weight into its shared-memory ring while the preceding kernel drains (the activations, the
+ *              bias and Y are only touched after that kernel has completed), and DEQUANT_MMA passes
+ *              GGUFB200_DEQUANT_SRC_STABLE to its dequant launch.  A kernel that does not signal programmatic completion early
+ *              (every torch / cuBLAS kernel) is complete before its successor starts, so the promise only excludes producers
+ *              of the packed bytes that execute griddepcontrol.launch_dependents before their last write. */
+#define GGUFB200_FLAG_W_STABLE 0x4000
 
 int ggufb200_version(void);
 const char *ggufb200_strerror(int rc);
@@ -107,7 +115,13 @@ int ggufb200_supported(int ggml_type, int op);
  *              reference default (`dequant_dtype=None`), the activation dtype reproduces
  *              `dequant_dtype="target"`, 2 an explicit float32.  Results are bit-identical
  *              to the reference for every (math_dtype, out_dtype) pair.
+ *              Optionally OR-ed with GGUFB200_DEQUANT_SRC_STABLE: the caller promises that no kernel still in flight on
+ *              `stream` writes the packed bytes (model weights: written once at load time).  The kernel is launched with
+ *              programmatic stream serialization; with the promise it fetches packed tiles and unpacks the first of them
+ *              into shared memory while the preceding kernel drains, and only its stores wait for that kernel (whatever
+ *              the preceding kernels read or wrote in `out` is complete before the first byte lands).  Same results.
  */
+#define GGUFB200_DEQUANT_SRC_STABLE 0x100
 int ggufb200_dequant(int ggml_type, const void *packed, int64_t n_blocks, void *out, int out_dtype,
                      int math_dtype, void *stream);
 
@@ -207,8 +221,8 @@ int ggufb200_gemm(const void *W, int64_t N, int64_t K, int64_t ldw, const void *
 int ggufb200_linear_plan(int ggml_type, int64_t M, int64_t N, int64_t K, size_t workspace_bytes, int algo, int *tile_rows, int *k_ranges,
                          int *kblocks_per_range, int *ctas);
 
-/* Benchmark-only launch knobs of the standalone dequant kernel (they never change routing or results):
- * key 0 = dequant CTAs per SM (0 = default), key 1 = programmatic dependent launch (default 1),
+/* Benchmark-only launch knobs (they never change routing or results):
+ * key 1 = programmatic dependent launch of the standalone dequant kernel (default 1),
  * key 2 = CTAs per SM of the small-M integer-pattern kernel (0 = planner picks).
  * Refused with GGUFB200_E_UNSUPPORTED unless the environment variable GGUFB200_ALLOW_TUNING=1 is set when the
  * library is first used; every other key is refused always (route selection is per call: GGUFB200_ALGO_* | GGUFB200_FLAG_*). */

@@ -27,7 +27,7 @@ CTAS = int(os.environ.get("GEMV2_CTAS", "0"))       # A/B of the CTAs-per-SM cho
 if CTAS:
     assert L.ggufb200_set_tuning(2, CTAS) == 0, "set GGUFB200_ALLOW_TUNING=1"
 ONLY = os.environ.get("GEMV_ROUTES", "").split(",") if os.environ.get("GEMV_ROUTES") else None
-ROUTES = (("gemv_fast", lib.ALGO_GEMV_FAST), ("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
+ROUTES = (("gemv_fast_ws", lib.ALGO_GEMV_FAST | lib.FLAG_W_STABLE), ("gemv_fast", lib.ALGO_GEMV_FAST), ("tmem", lib.ALGO_FUSED_TMEM), ("tmem_exact", lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W), ("gemv_exact", lib.ALGO_GEMV))
 side = torch.cuda.Stream()
 for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
     qt = gguf.GGMLQuantizationType[qname]
@@ -44,7 +44,7 @@ for qname in (sys.argv[1:] or ["Q4_K", "Q8_0", "Q5_K"]):
             x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
             y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             for name, algo in ROUTES:
-                if name == "gemv_fast" and qname not in ("Q4_K", "Q5_K"):
+                if name.startswith("gemv_fast") and qname not in ("Q4_K", "Q5_K"):
                     continue
                 if ONLY and name not in ONLY:
                     continue

@@ -16,6 +16,5 @@ if [ "$1" = "linear" ] || [ "$2" = "linear" ]; then
 fi
 if [ "$1" = "probe" ]; then
   timeout -k 10 300 python tools/probe_bw.py 2>&1 | tee gpurun_out/probe_bw.log
-  for c in 4 8; do timeout -k 10 200 python bench.py --steps 10 --warmup 3 --no-e2e --cpu-budget 0.3 --ctas-per-sm $c 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('ctas/sm', $c, d['value'], d['roofline']['per_qtype'])"; done
   timeout -k 10 400 ncu --set full --clock-control none --import-source on -k regex:dequant_kernel -s 113 -c 7 -o gpurun_out/prof_dequant_q4k_v2 python bench.py --steps 2 --warmup 3 --no-e2e --cpu-budget 0.3 > gpurun_out/ncu_bench2.log 2>&1
 fi

@@ -1,7 +1,7 @@
 #!/bin/bash
 # bench.py under a few launch-mode / tuning variants; prints value and roofline.frac per variant
 mkdir -p gpurun_out
-for v in "" "--no-pdl" "--graph" "--graph --no-pdl" "--ctas-per-sm 3" "--ctas-per-sm 2"; do
+for v in "" "--no-pdl" "--graph" "--graph --no-pdl"; do
   timeout -k 10 200 python bench.py --steps 20 --warmup 3 --no-e2e --cpu-budget 0.2 $v 2>gpurun_out/sweep.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
