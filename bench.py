@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tuning", default="", help="bench-only launch knobs, key=value[,key=value] (ggufb200_set_tuning)")
     ap.add_argument("--no-pdl", action="store_true", help="tuning knob: disable programmatic dependent launch")
     ap.add_argument("--no-src-stable", action="store_true", help="A/B: launch the dequant kernel without GGUFB200_DEQUANT_SRC_STABLE")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of replaying each step from a CUDA graph")
@@ -291,12 +292,15 @@ def main():
     import __graft_entry__ as ge
     import oracle  # only for the seeded synthetic block generator and the cpu_baseline leg
 
-    if args.no_pdl:
+    if args.no_pdl or args.tuning:
         os.environ["GGUFB200_ALLOW_TUNING"] = "1"      # benchmark-only launch knobs of the dequant kernel (never routing)
     dq, ops, rep = ge._sub("dequant"), ge._sub("ops"), ge._sub("replicas")
     lib = ge._sub("_lib").lib()        # raises if the CUDA extension is missing: no fallback
     if args.no_pdl and lib.ggufb200_set_tuning(1, 0) != 0:
         raise RuntimeError("tuning refused")
+    for kv in filter(None, args.tuning.split(",")):
+        if lib.ggufb200_set_tuning(int(kv.split("=")[0]), int(kv.split("=")[1])) != 0:
+            raise RuntimeError("tuning refused")
     rank, local_rank, world = rep.init()
     numa = rep.bind_to_gpu_numa(local_rank)     # before any pinned allocation: staging buffers land next to the GPU
     if world != args.gpus and rank == 0:

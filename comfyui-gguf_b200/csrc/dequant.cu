@@ -14,9 +14,11 @@
 //     profiles/r02_k1_variants_ab.log, same effect as in tools/probe_write.cu's plain-store probes.)
 //   * the tile is staged into shared memory by thread 0 with the TMA engine (cp.async.bulk, SASS UBLKCP), completion on
 //     an mbarrier that only thread 0 polls; the other threads sleep in the CTA barrier
-//   * every thread unpacks one run of 32 consecutive elements from shared memory (blocks.cuh) into a linear output
-//     tile in shared memory, which leaves through ONE bulk async store: every HBM write is a full line
+//   * every thread unpacks one run of 32 consecutive elements from shared memory (blocks.cuh) into its row of the output
+//     tile in shared memory, which leaves through ONE swizzled tensor-map store (cp.async.bulk.tensor.2d, SASS UTMASTG): no
+//     thread computes a global address, every HBM write is a full line, and the unpack runs with immediate offsets
 #include "blocks.cuh"
+#include "umma.cuh"
 
 namespace ggufb200 {
 
@@ -24,18 +26,22 @@ constexpr int kThreads = 128;       // threads per CTA of the dequant kernel = 4
 
 int g_dequant_pdl = 1;          // programmatic dependent launch of the dequant kernel; ggufb200_set_tuning(1, 0/1)
 
-// bulk async copy shared -> global (TMA engine), tracked with bulk async-groups
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+// Store into the OUTPUT tile.  No "memory" clobber: the output tile never aliases the packed tile the unpack reads, so the
+// compiler may keep the bytes it has already loaded (the high nibbles of a 4-bit block sit in the same bytes as the low ones)
+// across these stores; `volatile` keeps them in order before the fence + barrier that publish the tile.
+__device__ __forceinline__ void st_otile_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
-__device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// One thread = one run of 32 consecutive elements of the tile at `tile` (shared memory); results to the linear output tile.
+// One thread = one run of 32 consecutive elements of the packed tile at `tile` (shared memory).  The output tile is laid out for
+// a swizzled 2-D tensor-map store, one row per thread (fp16 / bf16: 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B; fp32: 128-byte rows,
+// SWIZZLE_128B): 16-byte chunk p of a row sits at chunk p ^ (address bits 7.. of the row), so the chunks are processed in their
+// natural order -- every byte offset and shift of the unpack is an immediate -- and the STS.128 of a quarter-warp still hit eight
+// different bank groups.  (A linear tile needs the chunk ORDER rotated per lane instead: dynamic offsets and shifts, 7-17 % more
+// instructions, 0.951 instead of 0.997 of the copy peak on the Flux-shape sweep -- profiles/r02_k1_variants_ab.log.)
 template <class Q, int MATH, int OUT>
-__device__ __forceinline__ void dequant_tile(const uint8_t *tile, uint8_t *otile, int tile_elems, int tid, int lane)
+__device__ __forceinline__ void dequant_tile(const uint8_t *tile, uint8_t *otile, int tile_elems, int tid)
 {
     constexpr int OB = OutT<OUT>::bytes;
     constexpr int EPC = 16 / OB;                           // elements per 16-byte chunk: 8 or 4
@@ -43,29 +49,25 @@ __device__ __forceinline__ void dequant_tile(const uint8_t *tile, uint8_t *otile
     constexpr int GROUP = GroupOf<Q>::value;
     const int blk_in_tile = (tid * 32) / Q::BS;
     const int e0 = (tid * 32) % Q::BS;
-    const int rot = (CH == 4) ? (lane >> 1) : lane;
     if (tid * 32 < tile_elems) {
         const uint8_t *blk = tile + blk_in_tile * Q::TS;
         const GroupScale<MATH> g0 = group_scale<Q, MATH>(blk, e0);
         GroupScale<MATH> g1 = g0;
         if constexpr (GROUP == 16) g1 = group_scale<Q, MATH>(blk, e0 + 16);
         const uint32_t obase = smem_u32(otile) + tid * (32 * OB);
+        const uint32_t sw = (obase >> 7) & (CH - 1);       // the engine's swizzle key: shared-memory address bits 7-8 (64B mode) / 7-9 (128B mode)
 #pragma unroll
-        for (int p = 0; p < CH; ++p) {
-            const int c = (p + rot) & (CH - 1);          // rotated chunk order: conflict-free STS.128
+        for (int c = 0; c < CH; ++c) {
             const int e = e0 + c * EPC;
             const bool second = (GROUP == 16) && (c * EPC >= 16);
-            GroupScale<MATH> g;
-            g.a = second ? g1.a : g0.a;
-            g.b = second ? g1.b : g0.b;
             typename Math<MATH>::T2 v[EPC / 2];
-            dequant_elems<Q, MATH, EPC>(blk, e, g, v);
+            dequant_elems<Q, MATH, EPC>(blk, e, second ? g1 : g0, v);
+            const uint32_t oaddr = obase + ((uint32_t)c ^ sw) * 16;
             if constexpr (OUT == kF32) {
                 float2 f0 = Math<MATH>::to_f32x2(v[0]), f1 = Math<MATH>::to_f32x2(v[1]);
-                st_shared_v4(obase + c * 16, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
+                st_otile_v4(oaddr, __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f1.x), __float_as_uint(f1.y));
             } else {
-                st_shared_v4(obase + c * 16, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]),
-                             pack16<OUT, MATH>(v[3]));
+                st_otile_v4(oaddr, pack16<OUT, MATH>(v[0]), pack16<OUT, MATH>(v[1]), pack16<OUT, MATH>(v[2]), pack16<OUT, MATH>(v[3]));
             }
         }
     }
@@ -74,8 +76,8 @@ __device__ __forceinline__ void dequant_tile(const uint8_t *tile, uint8_t *otile
 // One tile per CTA (see the file header).  flags: bit 0 = the packed pointer is 16-byte aligned (bulk copy legal),
 // bit 1 = GGUFB200_DEQUANT_SRC_STABLE.
 template <class Q, int MATH, int OUT, int THREADS>
-__global__ void __launch_bounds__(THREADS) dequant_kernel(const uint8_t *__restrict__ src, void *__restrict__ dst, long long n_blocks,
-                                                              int flags)
+__global__ void __launch_bounds__(THREADS) dequant_kernel(const __grid_constant__ CUtensorMap tmOut, const uint8_t *__restrict__ src,
+                                                          void *__restrict__ dst, long long n_blocks, int flags)
 {
     constexpr int OB = OutT<OUT>::bytes;
     constexpr int TILE_ELEMS = THREADS * 32;
@@ -86,13 +88,14 @@ __global__ void __launch_bounds__(THREADS) dequant_kernel(const uint8_t *__restr
     const int bulk_ok = flags & 1;
     const bool early = bulk_ok && (flags & 2);
 
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    uint8_t *tile = smem + 128;
-    uint8_t *otile = tile + TILE_BYTES + 16 + ((128 - ((TILE_BYTES + 16) & 127)) & 127);
+    // output tile first (the swizzle pattern of the tensor-map store is a function of the shared-memory ADDRESS bits; the
+    // threads derive their key from the address too, so the two agree wherever the window starts)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *otile = smem;
+    uint8_t *tile = smem + TILE_ELEMS * OB;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tile + ((TILE_BYTES + 16 + 15) & ~15));
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
     const long long t = blockIdx.x;
     const long long total_bytes = n_blocks * (long long)Q::TS;
     const long long n_elems = n_blocks * (long long)Q::BS;
@@ -121,12 +124,16 @@ __global__ void __launch_bounds__(THREADS) dequant_kernel(const uint8_t *__restr
     const long long elem_base = t * (long long)TILE_ELEMS;
     const long long left = n_elems - elem_base;
     const int tile_elems = left < TILE_ELEMS ? (int)left : TILE_ELEMS;
-    dequant_tile<Q, MATH, OUT>(tile, otile, tile_elems, tid, lane);
+    dequant_tile<Q, MATH, OUT>(tile, otile, tile_elems, tid);
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
         if (early) asm volatile("griddepcontrol.wait;" ::: "memory");
-        bulk_s2g(reinterpret_cast<uint8_t *>(dst) + elem_base * OB, otile, (uint32_t)(tile_elems * OB));
+        // one box = this tile's THREADS rows; rows past the end of the tensor (short last tile) are clipped by the TMA engine
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmOut)),
+                     "r"(smem_u32(otile)), "r"(0), "r"((int)(t * THREADS))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the shared-memory tile must outlive the engine's read of it
     }
 }
@@ -193,13 +200,29 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
 {
     constexpr int THREADS = kThreads;
     constexpr int TILE_BLOCKS = THREADS * 32 / Q::BS;
-    constexpr int TB = TILE_BLOCKS * Q::TS + 16;
-    constexpr int SMEM = 128 + TB + ((128 - (TB & 127)) & 127) + THREADS * 32 * OutT<OUT>::bytes;
+    constexpr int OB = OutT<OUT>::bytes;
+    constexpr int TB = ((TILE_BLOCKS * Q::TS + 16 + 15) & ~15);
+    constexpr int SMEM = THREADS * 32 * OB + TB + 16;
     auto kern = dequant_kernel<Q, MATH, OUT, THREADS>;
     static unsigned char smem_set[64] = {};
     if (!ensure_dynamic_smem(kern, SMEM, smem_set)) return GGUFB200_E_CUDA;
     const long long n_tiles = (n_blocks + TILE_BLOCKS - 1) / TILE_BLOCKS;
     if (n_tiles > 0x7fffffffll) return GGUFB200_E_SHAPE;
+    CUtensorMap tmOut{};
+    {
+        // the output as [runs of 32 elements][64 | 128 bytes]: one row per thread, one box of THREADS rows per tile
+        G2EncodeFn fn = g2_encode_fn();
+        const long long n_rows = n_blocks * (long long)Q::BS / 32;
+        if (!fn || n_rows > 0x7fffffffll) return GGUFB200_E_CUDA;
+        cuuint64_t dims[2] = {(cuuint64_t)(32 * OB), (cuuint64_t)n_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)(32 * OB)};
+        cuuint32_t box[2] = {(cuuint32_t)(32 * OB), (cuuint32_t)THREADS};
+        cuuint32_t estr[2] = {1, 1};
+        if (fn(&tmOut, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               OB == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return GGUFB200_E_CUDA;
+    }
     int flags = ((reinterpret_cast<uintptr_t>(packed) & 15) == 0) ? 1 : 0;
     if (src_stable) flags |= 2;
     cudaLaunchConfig_t cfg{};
@@ -212,7 +235,7 @@ template <class Q, int MATH, int OUT> static int launch_dequant(const void *pack
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_dequant_pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, reinterpret_cast<const uint8_t *>(packed), out, (long long)n_blocks, flags);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmOut, reinterpret_cast<const uint8_t *>(packed), out, (long long)n_blocks, flags);
     return e == cudaSuccess ? GGUFB200_OK : GGUFB200_E_CUDA;
 }
 

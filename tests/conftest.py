@@ -29,6 +29,11 @@ def pytest_collection_modifyitems(config, items):
 def pkg():
     import __graft_entry__ as ge
     ge.load_package()
+    # A/B runs of kernel variants (tools/gpu_*.sh only): GGUFB200_ALLOW_TUNING=1 GGUFB200_TEST_TUNING="key=value[,key=value]"
+    # runs the suite with bench-only launch knobs set.  Never set in the driver's runs.
+    for kv in filter(None, os.environ.get("GGUFB200_TEST_TUNING", "").split(",")):
+        k, v = kv.split("=")
+        assert ge._sub("_lib").lib().ggufb200_set_tuning(int(k), int(v)) == 0
 
     class NS:
         lib = ge._sub("_lib")
