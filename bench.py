@@ -237,17 +237,26 @@ def run_reference(args):
     import oracle
     import gguf
     pick_oracle_threads()   # torchrun sets OMP_NUM_THREADS=1 for its workers: choose the team size explicitly
-    N, K = 3072, 3072
+    # the SAME workload as our arm: all 35 tensors (5 qtypes x 7 Flux shapes) per step, fp16 math, fp16 out -- 3.88 GB of
+    # algorithmic bytes per step, about 0.3 - 1.5 s on the host cores, so the default --steps 20 --warmup 3 ends within a minute
     tensors = []
-    for q in QTYPES:
+    n_elems = 0
+    for qi, q in enumerate(QTYPES):
         qt = gguf.GGMLQuantizationType[q]
         bs, ts = gguf.GGML_QUANT_SIZES[qt]
-        tensors.append((q, int(qt), oracle.random_blocks(int(qt), N * K // bs, seed=42)))
-    per_step = sum(alg_bytes(q, N * K) for q, _, _ in tensors)
+        for si, (N, K) in enumerate(FLUX_SHAPES[:max(1, args.ref_shapes)]):
+            n_blocks = N * K // bs
+            chunk = min(n_blocks, 1 << 15)
+            raw = oracle.random_blocks(int(qt), chunk, seed=100 * qi + si)
+            reps = (n_blocks + chunk - 1) // chunk
+            out = np.zeros(N * K, dtype=np.uint16)         # preallocated and touched, like the GPU arm's output buffers
+            tensors.append((q, int(qt), np.ascontiguousarray(np.tile(raw, (reps, 1))[:n_blocks]).reshape(-1), N * K, out))
+            n_elems += N * K
+    per_step = sum(alg_bytes(q, n) for q, _, _, n, _ in tensors)
 
     def step():
-        for _, code, raw in tensors:
-            oracle.dequant(raw, code, oracle.DT_F16, oracle.DT_F16)
+        for _, code, raw, _n, out in tensors:
+            oracle.dequant(raw, code, oracle.DT_F16, oracle.DT_F16, out=out)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -255,12 +264,15 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt / 1e9
-    sample = (f"each step = the [3072,3072] member of the sweep for {'/'.join(QTYPES)} (bounded sample of the configs[1] workload), "
-              "C oracle port of dequant.py, OpenMP")
+    sample = (f"each step = {'the whole' if len(tensors) == len(QTYPES) * len(FLUX_SHAPES) else 'a subset of the'} configs[1] workload "
+              f"({len(tensors)} tensors: {'/'.join(QTYPES)} x {len(tensors) // len(QTYPES)} Flux shapes, {per_step / 1e9:.2f} GB algorithmic), "
+              "C oracle port of dequant.py, OpenMP, all host threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "data": "synthetic", "impl_note": "reference arm = the reference's algorithm on the host cores (tier contract): oracle/gguf_oracle.c",
+        "config": {"workload": WORKLOAD, "tensors_per_step": len(tensors), "elements_per_step": n_elems, "algorithmic_bytes_per_step": per_step,
+                   "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -274,6 +286,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--ref-shapes", type=int, default=len(FLUX_SHAPES), help="--impl reference: shapes per qtype (default: all 7 = the whole workload; tests use 1)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tuning", default="", help="bench-only launch knobs, key=value[,key=value] (ggufb200_set_tuning)")
     ap.add_argument("--no-pdl", action="store_true", help="tuning knob: disable programmatic dependent launch")
@@ -481,7 +494,7 @@ def main():
     # ---------------- e2e through the plugin call with HOST buffers
     e2e = None
     if not args.no_e2e:
-        sub = [t for t in tensors if t["shape"] == (3072, 3072) or t["shape"] == (9216, 3072)]   # 10 tensors, ~0.19 G elements
+        sub = list(tensors)      # the whole workload: 35 tensors, 1.05 GB in + 2.83 GB out per step through pinned host buffers
         pin_in = [t["host"].pin_memory() for t in sub]
         pin_out = [torch.empty(t["shape"], dtype=torch.float16).pin_memory() for t in sub]
         h2d = sum(p.numel() for p in pin_in)
@@ -527,7 +540,7 @@ def main():
         e2e = {"value": tot / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k2,
                "ms_per_step": ms / k2,
                "what": "dequantize_tensor(GGMLTensor in pinned host memory) -> fp16 result copied back to pinned host memory, "
-                       "for the [3072,3072] and [9216,3072] tensors of all 5 qtypes (10 tensors per step), tensors issued round-robin on 3 CUDA streams"}
+                       "for all 35 tensors of the step (the same workload as `value`), tensors issued round-robin on 3 CUDA streams"}
 
     n_tensors = len(tensors)
     # ---------------- secondary BASELINE metric: Flux.1-dev-shape Q4_K_S 1024px denoise step, ours vs the reference's torch chain

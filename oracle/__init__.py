@@ -54,13 +54,16 @@ def type_info(qtype: int) -> tuple[int, int]:
     return bs.value, ts.value
 
 
-def dequant(packed: np.ndarray, qtype: int, out_dtype: int = DT_F16, math_dtype: int = DT_F16) -> np.ndarray:
-    """Dequantise a flat uint8 block stream.  fp16/bf16 results come back as raw uint16 bit patterns."""
+def dequant(packed: np.ndarray, qtype: int, out_dtype: int = DT_F16, math_dtype: int = DT_F16, out: np.ndarray | None = None) -> np.ndarray:
+    """Dequantise a flat uint8 block stream.  fp16/bf16 results come back as raw uint16 bit patterns.
+    `out`: optional preallocated flat result array (bench.py's reference arm reuses its output buffers like the GPU arm does)."""
     packed = np.ascontiguousarray(packed, dtype=np.uint8).reshape(-1)
     bs, ts = type_info(qtype)
     assert packed.size % ts == 0, (packed.size, ts)
     n_blocks = packed.size // ts
-    out = np.empty(n_blocks * bs, dtype=_NP_OUT[out_dtype])
+    if out is None:
+        out = np.empty(n_blocks * bs, dtype=_NP_OUT[out_dtype])
+    assert out.dtype == _NP_OUT[out_dtype] and out.size == n_blocks * bs and out.flags.c_contiguous
     rc = lib().ggor_dequant(int(qtype), packed.ctypes.data, n_blocks, out.ctypes.data, out_dtype, math_dtype)
     if rc != 0:
         raise RuntimeError(f"oracle dequant failed rc={rc}")

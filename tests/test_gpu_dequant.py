@@ -128,3 +128,74 @@ def test_row_gather_matches_full_dequant(pkg, qt):
     full = pkg.dequant.dequantize_tensor(t, torch.bfloat16)
     assert tuple(got.shape) == (2, 3, K)
     assert torch.equal(got, full[idx])
+
+
+@pytest.mark.parametrize("qt", [Q.Q4_0, Q.Q8_0, Q.Q4_K, Q.Q6_K, Q.Q3_K, Q.IQ4_XS], ids=lambda q: q.name)
+def test_src_stable_flag_changes_nothing_but_the_launch(pkg, qt):
+    """GGUFB200_DEQUANT_SRC_STABLE (include/ggufb200.h) only moves the griddepcontrol.wait: same bits with and without it,
+    also for short last tiles and for a 16-byte-misaligned source (the flag is ignored there)."""
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    for n_blocks in ((5, 16 * 7 + 3) if bs == 256 else (130, 128 * 9 + 77)):
+        raw = oracle.random_blocks(int(qt), n_blocks, seed=11 + n_blocks)
+        want = oracle.dequant(raw, int(qt), oracle.DT_F16, oracle.DT_F16)
+        dev_raw = torch.from_numpy(raw).to(DEV)
+        for stable in (False, True):
+            out = pkg.dequant.dequantize(dev_raw, qt, (n_blocks * bs,), src_stable=stable)
+            assert np.array_equal(canon_nan(torch_bits(out), 0), canon_nan(want, 0)), (qt.name, n_blocks, stable)
+        shifted = torch.empty(raw.size + 2, dtype=torch.uint8, device=DEV)[2:]
+        shifted.copy_(dev_raw.reshape(-1))
+        out = pkg.dequant.dequantize(shifted, qt, (n_blocks * bs,), src_stable=True)
+        assert np.array_equal(canon_nan(torch_bits(out), 0), canon_nan(want, 0)), (qt.name, n_blocks, "misaligned")
+
+
+def test_back_to_back_launches_into_one_buffer_keep_stream_order(pkg):
+    """Programmatic dependent launch lets a dequant kernel start (fetch + unpack) under its predecessor's tail; its STORES must
+    still wait.  A CUDA graph of 24 raw launches alternates two different packed tensors into ONE output buffer, with a
+    device-side copy of the buffer after every launch: every copy must hold exactly the tensor launched just before it."""
+    L, lib = pkg.lib.lib(), pkg.lib
+    qt = Q.Q4_K
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    n_blocks = 16 * 600 + 5                   # 601 tiles: several waves of CTAs, short last tile
+    raws = [oracle.random_blocks(int(qt), n_blocks, seed=s) for s in (1, 2)]
+    wants = [oracle.dequant(r, int(qt), oracle.DT_F16, oracle.DT_F16) for r in raws]
+    devs = [torch.from_numpy(r).to(DEV) for r in raws]
+    out = torch.zeros(n_blocks * bs, dtype=torch.float16, device=DEV)
+    snaps = [torch.empty_like(out) for _ in range(24)]
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+
+    def enqueue(st):
+        for i in range(24):
+            rc = L.ggufb200_dequant(int(qt), devs[i & 1].data_ptr(), n_blocks, out.data_ptr(), 0, lib.DEQUANT_SRC_STABLE, st.cuda_stream)
+            assert rc == 0
+            with torch.cuda.stream(st):
+                snaps[i].copy_(out)
+    with torch.cuda.stream(side):
+        enqueue(side)           # eager once (also warms the kernels before capture)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        enqueue(side)
+    for s in snaps:
+        s.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for i, s in enumerate(snaps):
+        assert np.array_equal(torch_bits(s), wants[i & 1]), f"launch {i}: the buffer does not hold the tensor launched last"
+
+
+def test_consecutive_dequants_without_a_kernel_between_them(pkg):
+    """Same as above with NOTHING between the launches (kernel -> kernel programmatic edges only): the last writer wins."""
+    L, lib = pkg.lib.lib(), pkg.lib
+    qt = Q.Q8_0
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    n_blocks = 128 * 700 + 9
+    raws = [oracle.random_blocks(int(qt), n_blocks, seed=s) for s in (5, 6, 7)]
+    devs = [torch.from_numpy(r).to(DEV) for r in raws]
+    out = torch.zeros(n_blocks * bs, dtype=torch.float16, device=DEV)
+    st = torch.cuda.current_stream()
+    for rounds in range(3):
+        for i in range(9):
+            assert L.ggufb200_dequant(int(qt), devs[i % 3].data_ptr(), n_blocks, out.data_ptr(), 0, lib.DEQUANT_SRC_STABLE, st.cuda_stream) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(torch_bits(out), oracle.dequant(raws[2], int(qt), oracle.DT_F16, oracle.DT_F16))

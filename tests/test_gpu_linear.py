@@ -310,6 +310,11 @@ def test_gemv_fast_kernel_vs_oracle_and_ideal(pkg, qt, dt, code, M, N, K):
     bias = torch.randn(N, device=DEV, dtype=torch.float32) * 0.1
     y = pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_GEMV_FAST)
     assert torch.equal(y, pkg.ops.linear_packed(x, w, bias, None, pkg.lib.ALGO_GEMV_FAST)), "fixed summation order: reproducible"
+    # W_STABLE only lets the weight ring fill before the preceding kernel has drained: same bits, also back to back with a
+    # kernel that has just written the activations
+    for _ in range(3):
+        x2 = x + 0
+        assert torch.equal(y, pkg.ops.linear_packed(x2, w, bias, None, pkg.lib.ALGO_GEMV_FAST | pkg.lib.FLAG_W_STABLE))
     want = oracle.linear(raw, int(qt), N, K, torch_bits(x), code, oracle.DT_F16, torch_bits(bias.to(dt)))
     ref = torch.from_numpy(bits_to_f32(want.reshape(-1), code).reshape(M, N)).to(DEV)
     assert rel_fro(y.float().cpu().numpy(), ref.cpu().numpy()) <= (1e-3 if dt == torch.float16 else 8e-3)
