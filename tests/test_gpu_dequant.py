@@ -199,3 +199,27 @@ def test_consecutive_dequants_without_a_kernel_between_them(pkg):
             assert L.ggufb200_dequant(int(qt), devs[i % 3].data_ptr(), n_blocks, out.data_ptr(), 0, lib.DEQUANT_SRC_STABLE, st.cuda_stream) == 0
         torch.cuda.synchronize()
         assert np.array_equal(torch_bits(out), oracle.dequant(raws[2], int(qt), oracle.DT_F16, oracle.DT_F16))
+
+
+def test_src_stable_after_a_torch_kernel_that_writes_the_packed_bytes(pkg):
+    """dequantize() passes SRC_STABLE by default (dequant.py): the packed bytes come from loads, copies or ordinary torch
+    kernels, which do not signal programmatic completion early, so they are complete before our kernel starts.  Here a torch
+    kernel rewrites a 37 MB packed tensor IN PLACE and the dequant follows immediately on the same stream, 24 times with
+    different contents: the result must always be the dequant of the new bytes."""
+    qt = Q.Q4_K
+    bs, ts = gguf.GGML_QUANT_SIZES[qt]
+    n_blocks = 21504 * 3072 // bs
+    seed = oracle.random_blocks(int(qt), 1 << 12, seed=21, scale=0.02)
+    base = torch.from_numpy(seed).to(DEV).repeat(n_blocks // (1 << 12), 1).contiguous()
+    # flipping quant bytes only (offsets >= 16) keeps every fp16 field finite
+    mask = torch.zeros(ts, dtype=torch.uint8, device=DEV)
+    work = base.clone()
+    torch.cuda.synchronize()
+    for i in range(24):
+        mask.zero_()
+        mask[16 + (i * 5) % 128] = 1 + (i % 255)
+        torch.bitwise_xor(base, mask, out=work)                          # the writer: an ordinary torch kernel over 37 MB
+        got = pkg.dequant.dequantize(work, qt, (n_blocks * bs,), src_stable=True)
+        torch.cuda.synchronize()
+        want = pkg.dequant.dequantize(work, qt, (n_blocks * bs,), src_stable=False)
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16)), f"iteration {i}: stale packed bytes were read"
