@@ -94,6 +94,10 @@ def main():
             routes = {
                 "tmem": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | nosplit),
                 "tmem384": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE384 | nosplit),
+                "tmem192": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE192 | nosplit),
+                "tmem_ns": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_NOSPLIT),
+                "tmem192_ns": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE192 | lib.FLAG_NOSPLIT),
+                "tmem384_ns": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_TILE384 | lib.FLAG_NOSPLIT),
                 "tmem_exact": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W | nosplit),
                 "tmem384_exact": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | lib.FLAG_EXACT_W | lib.FLAG_TILE384 | nosplit),
                 "tmem_spans": lambda: ops.linear_packed(x, nxt(), None, None, lib.ALGO_FUSED_TMEM | nosplit, use_spans=True),
