@@ -8,14 +8,14 @@ tensors (35 kernel launches, 1.42 G elements, 1.05 GB packed read + 2.83 GB writ
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 value      algorithmic GB/s (packed bytes read + output bytes written) / device time, inputs resident in HBM
-e2e        same metric through the plugin call (`dequantize_tensor`) with HOST buffers: pinned-host packed bytes
-           -> H2D -> kernel -> D2H of the result, copies inside the timed region
-roofline   HBM roofline of the dequant kernel: algorithmic bytes per launch / mean launch time (CUDA events
-           around every launch) against MEASURED_PEAKS.json hbm_gbs
+e2e        same metric and the same 35 tensors through the plugin call (`dequantize_tensor`) with HOST buffers: pinned-host
+           packed bytes -> H2D -> kernel -> D2H of the result, copies inside the timed region
+roofline   HBM roofline of the dequant kernel: algorithmic bytes per launch / (CUDA-event time of the timed region / launches
+           in it) against MEASURED_PEAKS.json hbm_gbs; per-qtype back-to-back and per-launch event-pair figures beside it
 cpu_baseline  the C oracle port of the reference algorithm on the host cores (bounded sample), plus gguf-py numpy
 N > 1      independent replicas (one process per GPU, torchrun), no collective on the data path; value = sum of
            units / max-over-ranks device time  ("scaling": "weak")
---impl reference   times the reference's CPU algorithm (oracle port, all host threads) on a bounded sample
+--impl reference   times the reference's CPU algorithm (oracle port, all host threads) on the same 35 tensors per step
 """
 from __future__ import annotations
 
