@@ -276,8 +276,10 @@ int dequant_dispatch(int type, const void *packed, long long n_blocks, void *out
     case T_IQ4_NL: return dispatch_math<Block<T_IQ4_NL>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
     case T_IQ4_XS: return dispatch_math<Block<T_IQ4_XS>>(packed, n_blocks, out, out_dtype, math_dtype, stable, st);
     case T_BF16: {
+        // one 8-element vector per thread, CTAs in address order (the grid-stride loop of the kernel only runs past the first
+        // iteration for tensors beyond 2^31 CTAs): same reasoning as for the block formats above
         long long blocks = (n_blocks + (long long)kThreads * 8 - 1) / ((long long)kThreads * 8);
-        long long cap = (long long)sm_count() * 8;
+        long long cap = 0x7fffffffll;
         unsigned grid = (unsigned)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
         const uint16_t *s = reinterpret_cast<const uint16_t *>(packed);
         if (out_dtype == kF16) bf16_kernel<kF16><<<grid, kThreads, 0, st>>>(s, out, n_blocks);
