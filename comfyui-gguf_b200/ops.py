@@ -440,7 +440,10 @@ class GGMLOps(comfy_ops.manual_cast):
         lora_in_kernel = True
 
         def _lora_operands(self, terms, dev, dtype):
-            key = tuple((id(up), id(down), float(scale)) for scale, up, down in terms) + (str(dev), dtype)
+            # identity + storage + version of every factor: a patch set that was swapped for another one (even at a recycled
+            # id()) or modified in place rebuilds the operands
+            key = tuple((id(up), up.data_ptr(), up._version, tuple(up.shape), id(down), down.data_ptr(), down._version, float(scale))
+                        for scale, up, down in terms) + (str(dev), dtype)
             cached = self.__dict__.get("_gg_lora")
             if cached is not None and cached[0] == key:
                 return cached[1], cached[2]
