@@ -437,7 +437,12 @@ class GGMLOps(comfy_ops.manual_cast):
         # LoRA inside the fused kernel (csrc/gemm4.cu: one extra k-block): U = scale * up (fp16 [N, 64]) and
         # down (act dtype [64, K]), zero padded to rank 64 and cached per patch set; per forward only T = x * down^T
         # ([M, 64], this package's dense tcgen05 GEMM) is computed before the fused call.
-        lora_in_kernel = True
+        # OPT-IN (default False = the side-GEMM route below): with several patched forwards queued back to back the in-kernel
+        # route hung intermittently on the B200 box (3 of 5 runs of tools/bench_flux.py --lora 32 without a synchronise between
+        # forwards, with and without programmatic dependent launch; every per-layer test and every synchronised run passes) --
+        # an unresolved race, DESIGN.md section 4 "LoRA".  The side-GEMM route runs the unpatched fused kernel plus two library
+        # GEMMs of rank sum(r).
+        lora_in_kernel = False
 
         def _lora_operands(self, terms, dev, dtype):
             # identity + storage + version of every factor: a patch set that was swapped for another one (even at a recycled

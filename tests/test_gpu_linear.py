@@ -154,17 +154,18 @@ def test_lora_on_packed_weight_runs_as_side_gemms(pkg, M, N, K, dtype, n_loras, 
     lin, x, ref, ideal = _lora_case(pkg, M, N, K, dtype, n_loras)
     assert lin._lora_terms(x.device), "LoRA-only patch list must be recognised"
     if numerics == "fast":
-        # default contract: base product AND the rank-r update run inside the TMEM-fed kernel (one extra k-block: U = scale*up
-        # rows in tensor memory, T = x*down^T TMA-fed); same budget against the reference arithmetic, and within bf16 / fp16
-        # output rounding of the side-GEMM formulation
-        y_in = lin(x)
-        assert "_gg_lora" in lin.__dict__, "the LoRA operands should have been prepared for the in-kernel path"
-        assert _rel(y_in, ref) <= (3e-3 if dtype == torch.float16 else 1e-2)
-        lin.lora_in_kernel = False
+        # opt-in route (GGMLOps.Linear.lora_in_kernel = True): base product AND the rank-r update inside the TMEM-fed kernel (one
+        # extra k-block: U = scale*up rows in tensor memory, T = x*down^T TMA-fed); same budget against the reference arithmetic,
+        # and within bf16 / fp16 output rounding of the side-GEMM formulation (the default)
+        y_side = lin(x)
+        lin.lora_in_kernel = True
         try:
-            y_side = lin(x)
+            y_in = lin(x)
+            torch.cuda.synchronize()
         finally:
             del lin.lora_in_kernel
+        assert "_gg_lora" in lin.__dict__, "the LoRA operands should have been prepared for the in-kernel path"
+        assert _rel(y_in, ref) <= (3e-3 if dtype == torch.float16 else 1e-2)
         assert _rel(y_in, y_side.double()) <= (1.5e-3 if dtype == torch.float16 else 8e-3)
     lin.linear_numerics = "exact"
     y = lin(x)

@@ -10,6 +10,10 @@ import sys
 import numpy as np
 import torch
 
+if os.environ.get("GGUFB200_DEBUG_HANG"):           # diagnostics: dump every thread's Python stack after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ["GGUFB200_DEBUG_HANG"]), exit=False)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -68,7 +72,7 @@ ROUTE_NAMES = {"exact": "fused dequant -> TMEM -> tcgen05 (gemm4, persistent), r
 
 
 def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=512, img_tokens=4096, device="cuda:0", numerics="exact",
-        block_qtype="Q4_K", batch=1, lora_rank=0):
+        block_qtype="Q4_K", batch=1, lora_rank=0, lora_in_kernel=False):
     ops_mod, lib = ge._sub("ops"), ge._sub("_lib")
     ops_mod.GGMLOps.Linear.linear_numerics = numerics
     dev = torch.device(device)
@@ -110,18 +114,27 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
                     down = (torch.randn(lora_rank, K, generator=g) * 0.02).to(dev, torch.bfloat16)
                     mod.weight.patches = [([(0.8, ("lora", (up, down, float(lora_rank), None, None, None)), 1.0, None, None)], "w")]
                     n_patched += 1
-            y_l = ours(**inp)
-            ms_in, _ = time_steps(lambda: ours(**inp), steps, warmup)
-            ops_mod.GGMLOps.Linear.lora_in_kernel = False
-            try:
-                y_s = ours(**inp)
-                ms_side, _ = time_steps(lambda: ours(**inp), steps, warmup)
-            finally:
+            print(f"lora: {n_patched} Linears patched", file=sys.stderr, flush=True)
+            # default route: the unpatched fused kernel + two side GEMMs of rank R (GGMLOps.Linear.lora_in_kernel = False)
+            y_s = ours(**inp)
+            ms_side, _ = time_steps(lambda: ours(**inp), steps, warmup)
+            print("lora: side-GEMM timing done", file=sys.stderr, flush=True)
+            lora = {"rank": lora_rank, "patched_linears": n_patched, "ms_per_step_side_gemms": ms_side, "side_gemms_over_unpatched": ms_side / ms_ours,
+                    "output_rel_diff_vs_unpatched": float(((y_s.float() - y_ours.float()).norm() / y_ours.float().norm()).item())}
+            if lora_in_kernel:
+                # opt-in route (one extra k-block of the fused kernel); a synchronise after every forward: see ops.py
                 ops_mod.GGMLOps.Linear.lora_in_kernel = True
-            lora = {"rank": lora_rank, "patched_linears": n_patched, "ms_per_step_in_kernel": ms_in, "ms_per_step_side_gemms": ms_side,
-                    "in_kernel_over_unpatched": ms_in / ms_ours, "side_gemms_over_unpatched": ms_side / ms_ours,
-                    "output_rel_diff_in_kernel_vs_side_gemms": float(((y_l.float() - y_s.float()).norm() / y_s.float().norm()).item()),
-                    "output_rel_diff_vs_unpatched": float(((y_l.float() - y_ours.float()).norm() / y_ours.float().norm()).item())}
+                try:
+                    def fwd_sync():
+                        y = ours(**inp)
+                        torch.cuda.synchronize()
+                        return y
+                    y_l = fwd_sync()
+                    ms_in, _ = time_steps(fwd_sync, steps, warmup)
+                finally:
+                    ops_mod.GGMLOps.Linear.lora_in_kernel = False
+                lora.update({"ms_per_step_in_kernel": ms_in, "in_kernel_over_unpatched": ms_in / ms_ours,
+                             "output_rel_diff_in_kernel_vs_side_gemms": float(((y_l.float() - y_s.float()).norm() / y_s.float().norm()).item())})
             for mod in ours.modules():
                 if isinstance(mod, ops_mod.GGMLOps.Linear) and ops_mod.is_quantized(mod.weight):
                     mod.weight.patches = []
@@ -150,5 +163,6 @@ if __name__ == "__main__":
     ap.add_argument("--numerics", default="exact", choices=["fast", "exact"])
     ap.add_argument("--qtype", default="Q4_K")
     ap.add_argument("--lora", type=int, default=0, help="also time the step with a rank-R LoRA on every quantised Linear")
+    ap.add_argument("--lora-in-kernel", action="store_true", help="also time the opt-in in-kernel LoRA route (synchronised forwards)")
     a = ap.parse_args()
-    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype, lora_rank=a.lora)))
+    print(json.dumps(run(a.depth, a.depth_single, a.steps, 3, a.ref_steps, a.txt, numerics=a.numerics, block_qtype=a.qtype, lora_rank=a.lora, lora_in_kernel=a.lora_in_kernel)))
