@@ -124,10 +124,14 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
             if lora_in_kernel:
                 # opt-in route (one extra k-block of the fused kernel); a synchronise after every forward: see ops.py
                 ops_mod.GGMLOps.Linear.lora_in_kernel = True
+                nosync = bool(os.environ.get("GGUFB200_LORA_NOSYNC"))             # diagnostics of the intermittent hang
+                if os.environ.get("GGUFB200_LORA_T_TORCH"):                        # diagnostics: T = x * down^T by the library GEMM
+                    ops_mod.linear_dense = lambda x, w, b=None: torch.nn.functional.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype))
                 try:
                     def fwd_sync():
                         y = ours(**inp)
-                        torch.cuda.synchronize()
+                        if not nosync:
+                            torch.cuda.synchronize()
                         return y
                     y_l = fwd_sync()
                     ms_in, _ = time_steps(fwd_sync, steps, warmup)
