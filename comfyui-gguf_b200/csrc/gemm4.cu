@@ -341,16 +341,23 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         };
         for (int item = pair; item < p.n_items; item += n_pairs) {
             const G4Item w = g4_item(p, item);
+            // Group g produces the k-blocks whose GLOBAL index is == g (mod 4), so it is the only writer of the A stages == g
+            // (mod 4) for the whole kernel: the parity wait on empty_a below can then never be satisfied by a phase two uses old.
+            // A LoRA k-block shifts the next item's first index off a multiple of 4; with the quarter taken from the ITEM-local
+            // index (round 2's first version: quarter g) another group became the next writer of a stage and, whenever the MMA
+            // warp lagged by more than one use, passed the wait on a stale phase -- the intermittent hang of the in-kernel LoRA
+            // route (profiles/r02_lora_in_kernel_intermittent_hang.log).
+            const int qr = (g - it0) & 3;                    // this group's quarter of every span of the item
             for (int i = 0; i < w.nspans; ++i, ++sp) {
                 const int b = sp % NP;
-                const int it = it0 + 4 * i + g;              // global k-block index of this group's quarter of the span
+                const int it = it0 + 4 * i + qr;             // global k-block index of this group's quarter of the span: == g (mod 4)
                 const int sa = it % AST;
                 mbar_wait(&full_p[b], (uint32_t)((sp / NP) & 1));
                 mbar_wait(&empty_a[sa], (uint32_t)(((it / AST) & 1) ^ 1));
                 g2_fence_after();
                 const uint8_t *src = packed + b * Cfg::P_BYTES + row * PITCH;
                 const uint32_t taddr = lane_base + (uint32_t)(sa * 32);
-                Prod::run64(src, g, [&](int half, const uint32_t (&o)[16]) { store_half(taddr, half, o); });
+                Prod::run64(src, qr, [&](int half, const uint32_t (&o)[16]) { store_half(taddr, half, o); });
                 g4_tmem_st_wait();
                 g2_fence_before();
                 __syncwarp();
@@ -359,7 +366,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_arrive(&empty_p[b]);
                 }
             }
-            if (w.lora && g == 0) {
+            if (w.lora && g == ((it0 + 4 * w.nspans) & 3)) {          // the group that owns the stage of the LoRA k-block's global index
                 // LoRA k-block: this row of U = scale * up (64 fp16, zero padded beyond the rank) straight from global memory
                 const int it = it0 + 4 * w.nspans;
                 const int sa = it % AST;

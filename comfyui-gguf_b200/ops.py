@@ -437,12 +437,13 @@ class GGMLOps(comfy_ops.manual_cast):
         # LoRA inside the fused kernel (csrc/gemm4.cu: one extra k-block): U = scale * up (fp16 [N, 64]) and
         # down (act dtype [64, K]), zero padded to rank 64 and cached per patch set; per forward only T = x * down^T
         # ([M, 64], this package's dense tcgen05 GEMM) is computed before the fused call.
-        # OPT-IN (default False = the side-GEMM route below): with several patched forwards queued back to back the in-kernel
-        # route hung intermittently on the B200 box (3 of 5 runs of tools/bench_flux.py --lora 32 without a synchronise between
-        # forwards, with and without programmatic dependent launch; every per-layer test and every synchronised run passes) --
-        # an unresolved race, DESIGN.md section 4 "LoRA".  The side-GEMM route runs the unpatched fused kernel plus two library
-        # GEMMs of rank sum(r).
-        lora_in_kernel = False
+        # (Round 2 shipped this route switched off for a few hours: with several patched forwards queued back to back it hung
+        # intermittently.  Cause: the LoRA k-block shifts the next item's first k-block index off a multiple of 4, and the
+        # producers took their quarter of a span from the item-local index, so a second group became the next writer of an A
+        # stage and could pass the empty-stage parity wait on a phase two uses old.  csrc/gemm4.cu now keys the quarter on the
+        # GLOBAL k-block index -- one writer group per stage, as without LoRA.  Evidence: profiles/r02_lora_in_kernel_*.log.)
+        # False -> the unpatched fused kernel plus two library GEMMs of rank sum(r) (`_add_lora`).
+        lora_in_kernel = True
 
         def _lora_operands(self, terms, dev, dtype):
             # identity + storage + version of every factor: a patch set that was swapped for another one (even at a recycled

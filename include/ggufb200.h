@@ -199,9 +199,8 @@ int ggufb200_linear_spans(int ggml_type, const void *W_packed, const void *W_spa
  * span, the T tile is TMA-fed like an activation tile): no second pass over Y, no extra GEMM launch for the up-projection.
  * algo must resolve to GGUFB200_ALGO_FUSED_TMEM (AUTO without EXACT_W on a weight that route supports, or explicit),
  * otherwise GGUFB200_E_UNSUPPORTED.  W_spans may be NULL.  fp16 dequant math.
- * KNOWN ISSUE (round 2): a model that issues many of these calls back to back without a stream synchronise hung
- * intermittently on B200 (profiles/r02_lora_in_kernel_intermittent_hang.log); single calls and synchronised sequences are
- * clean.  The Python layer therefore defaults to ggufb200_linear + two rank-R side GEMMs and keeps this entry point opt-in.
+ * (Round 2 fixed an intermittent hang of this entry point under many unsynchronised back-to-back calls: two producer groups
+ * could become writers of one A stage after the LoRA k-block; profiles/r02_lora_in_kernel_hang_and_fix.log.)
  */
 int ggufb200_linear_lora(int ggml_type, const void *W_packed, const void *W_spans, int64_t N, int64_t K, const void *X, int64_t M,
                          int64_t ldx, int act_dtype, const void *bias, int bias_dtype, const void *T, int64_t ldt, const void *U,

@@ -154,14 +154,13 @@ def test_lora_on_packed_weight_runs_as_side_gemms(pkg, M, N, K, dtype, n_loras, 
     lin, x, ref, ideal = _lora_case(pkg, M, N, K, dtype, n_loras)
     assert lin._lora_terms(x.device), "LoRA-only patch list must be recognised"
     if numerics == "fast":
-        # opt-in route (GGMLOps.Linear.lora_in_kernel = True): base product AND the rank-r update inside the TMEM-fed kernel (one
+        # default route (GGMLOps.Linear.lora_in_kernel = True): base product AND the rank-r update inside the TMEM-fed kernel (one
         # extra k-block: U = scale*up rows in tensor memory, T = x*down^T TMA-fed); same budget against the reference arithmetic,
-        # and within bf16 / fp16 output rounding of the side-GEMM formulation (the default)
-        y_side = lin(x)
-        lin.lora_in_kernel = True
+        # and within bf16 / fp16 output rounding of the side-GEMM formulation
+        y_in = lin(x)
+        lin.lora_in_kernel = False
         try:
-            y_in = lin(x)
-            torch.cuda.synchronize()
+            y_side = lin(x)
         finally:
             del lin.lora_in_kernel
         assert "_gg_lora" in lin.__dict__, "the LoRA operands should have been prepared for the in-kernel path"

@@ -115,14 +115,15 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
                     mod.weight.patches = [([(0.8, ("lora", (up, down, float(lora_rank), None, None, None)), 1.0, None, None)], "w")]
                     n_patched += 1
             print(f"lora: {n_patched} Linears patched", file=sys.stderr, flush=True)
-            # default route: the unpatched fused kernel + two side GEMMs of rank R (GGMLOps.Linear.lora_in_kernel = False)
+            # fallback route first: the unpatched fused kernel + two side GEMMs of rank R (GGMLOps.Linear.lora_in_kernel = False)
+            ops_mod.GGMLOps.Linear.lora_in_kernel = False
             y_s = ours(**inp)
             ms_side, _ = time_steps(lambda: ours(**inp), steps, warmup)
             print("lora: side-GEMM timing done", file=sys.stderr, flush=True)
             lora = {"rank": lora_rank, "patched_linears": n_patched, "ms_per_step_side_gemms": ms_side, "side_gemms_over_unpatched": ms_side / ms_ours,
                     "output_rel_diff_vs_unpatched": float(((y_s.float() - y_ours.float()).norm() / y_ours.float().norm()).item())}
             if lora_in_kernel:
-                # opt-in route (one extra k-block of the fused kernel); a synchronise after every forward: see ops.py
+                # default route (one extra k-block of the fused kernel); GGUFB200_LORA_NOSYNC=1 queues the forwards without a synchronise
                 ops_mod.GGMLOps.Linear.lora_in_kernel = True
                 nosync = bool(os.environ.get("GGUFB200_LORA_NOSYNC"))             # diagnostics of the intermittent hang
                 if os.environ.get("GGUFB200_LORA_T_TORCH"):                        # diagnostics: T = x * down^T by the library GEMM
@@ -136,9 +137,10 @@ def run(depth=19, depth_single=38, steps=10, warmup=3, ref_steps=3, txt_tokens=5
                     y_l = fwd_sync()
                     ms_in, _ = time_steps(fwd_sync, steps, warmup)
                 finally:
-                    ops_mod.GGMLOps.Linear.lora_in_kernel = False
+                    pass
                 lora.update({"ms_per_step_in_kernel": ms_in, "in_kernel_over_unpatched": ms_in / ms_ours,
                              "output_rel_diff_in_kernel_vs_side_gemms": float(((y_l.float() - y_s.float()).norm() / y_s.float().norm()).item())})
+            ops_mod.GGMLOps.Linear.lora_in_kernel = True
             for mod in ours.modules():
                 if isinstance(mod, ops_mod.GGMLOps.Linear) and ops_mod.is_quantized(mod.weight):
                     mod.weight.patches = []
