@@ -347,7 +347,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             // index (round 2's first version: quarter g) another group became the next writer of a stage and, whenever the MMA
             // warp lagged by more than one use, passed the wait on a stale phase -- the intermittent hang of the in-kernel LoRA
             // route (profiles/r02_lora_in_kernel_intermittent_hang.log).
-            const int qr = (g - it0) & 3;                    // this group's quarter of every span of the item
+            const int qr = g4_group_quarter(g, it0);         // this group's quarter of every span of the item (produce.cuh)
             for (int i = 0; i < w.nspans; ++i, ++sp) {
                 const int b = sp % NP;
                 const int it = it0 + 4 * i + qr;             // global k-block index of this group's quarter of the span: == g (mod 4)
@@ -366,7 +366,7 @@ gemm4_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_arrive(&empty_p[b]);
                 }
             }
-            if (w.lora && g == ((it0 + 4 * w.nspans) & 3)) {          // the group that owns the stage of the LoRA k-block's global index
+            if (w.lora && g == g4_lora_group(it0, w.nspans)) {       // the group that owns the stage of the LoRA k-block's global index
                 // LoRA k-block: this row of U = scale * up (64 fp16, zero padded beyond the rank) straight from global memory
                 const int it = it0 + 4 * w.nspans;
                 const int sa = it % AST;

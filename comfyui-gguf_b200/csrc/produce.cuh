@@ -340,4 +340,12 @@ template <bool FMA> struct FastProducer<Block<T_Q6_K>, FMA> {
     }
 };
 
+// ---------------------------------------------------------------- A-stage ownership of the TMEM-fed kernel (gemm4.cu)
+// The ring of A stages in tensor memory has a multiple of 4 stages and relies on ONE writer group per stage: producer group g
+// (0..3) writes exactly the k-blocks whose GLOBAL index is == g (mod 4), so the parity wait on a stage's `empty` barrier can
+// never be satisfied by a phase two uses old.  `it0` = global index of the item's first k-block (not a multiple of 4 once an
+// earlier item of this CTA pair carried a LoRA k-block).
+GG_HD int g4_group_quarter(int g, int it0) { return (g - it0) & 3; }                    // the group's quarter of every span of the item
+GG_HD int g4_lora_group(int it0, int nspans) { return (it0 + 4 * nspans) & 3; }         // the group that writes the LoRA k-block
+
 }  // namespace ggufb200

@@ -270,3 +270,35 @@ def test_fast_request_falls_back_to_generic_for_other_formats(hostf):
     assert hostf.hostf_produce(int(Q.Q3_K), buf.ctypes.data, 8, pitch, got.ctypes.data, 1) == 0
     want = oracle.dequant(raw.reshape(-1, 110), int(Q.Q3_K), oracle.DT_F16, oracle.DT_F16)
     assert _equal_mod_nan(got, want, oracle.DT_F16)
+
+
+# ---------------------------------------------------------------- gemm4: one writer group per A stage (the LoRA hang of round 2)
+def test_g4_one_writer_group_per_a_stage(hostf):
+    """csrc/gemm4.cu keeps dequantised k-blocks in a ring of A stages (a multiple of 4) and relies on ONE producer group per
+    stage: group g must write exactly the k-blocks whose global index is == g (mod 4), whatever mix of items with and without
+    a LoRA k-block a CTA pair walks through -- otherwise a parity wait on a stage can be satisfied by a phase two uses old
+    (profiles/r02_lora_in_kernel_hang_and_fix.log).  The MMA warp consumes the k-blocks of an item in order, so the k-block
+    with item-local index j must also be quarter j % 4 of span j / 4 (and the last one of a LoRA item the LoRA k-block)."""
+    hostf.hostf_g4_schedule.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n_items = int(rng.integers(1, 9))
+        nspans = rng.integers(1, 14, size=n_items).astype(np.int32)
+        lora = (rng.random(n_items) < (0.0 if trial % 4 == 0 else 0.6)).astype(np.int32)
+        total = int((4 * nspans + lora).sum())
+        writer = np.empty(total, dtype=np.int32)
+        quarter = np.empty(total, dtype=np.int32)
+        assert hostf.hostf_g4_schedule(nspans.ctypes.data, lora.ctypes.data, n_items, 0, writer.ctypes.data, quarter.ctypes.data, total) == 0
+        assert np.array_equal(writer, np.arange(total) % 4), (nspans, lora, writer)        # every index once, by group it % 4
+        it0 = 0
+        for n, l in zip(nspans, lora):                                                       # consumption order of the MMA warp
+            want = [j % 4 for j in range(4 * n)] + ([4] if l else [])
+            assert quarter[it0:it0 + len(want)].tolist() == want
+            it0 += len(want)
+    # the first round-2 mapping (quarter = group, LoRA by group 0) breaks the ownership as soon as an item follows a LoRA item
+    nspans = np.array([3, 3], dtype=np.int32)
+    lora = np.array([1, 0], dtype=np.int32)
+    writer = np.empty(25, dtype=np.int32)
+    quarter = np.empty(25, dtype=np.int32)
+    assert hostf.hostf_g4_schedule(nspans.ctypes.data, lora.ctypes.data, 2, 1, writer.ctypes.data, quarter.ctypes.data, 25) == 0
+    assert not np.array_equal(writer, np.arange(25) % 4)
