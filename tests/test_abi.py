@@ -153,3 +153,23 @@ def test_span_layout_geometry_without_gpu(pkg):
                                   pkg.lib.ALGO_FUSED_TMEM, None) == -5
     assert L.ggufb200_linear_lora(int(Q.Q4_K), p16, None, 8, 256, x, 4, 256, 1, None, 0, x, 48, x, x, 8, None, 0,
                                   pkg.lib.ALGO_FUSED_TMEM, None) == -3
+
+
+def test_python_constants_match_the_header(pkg):
+    """`_lib.py` mirrors the #define values of include/ggufb200.h by hand: every GGUFB200_ALGO_* / FLAG_* / dtype / op code and
+    the stable-source bits must agree (a drifted flag would silently select another route or drop a promise)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ggufb200.h")).read()
+    defines = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"^#define\s+GGUFB200_(\w+)\s+\(?(-?(?:0x[0-9A-Fa-f]+|\d+))\)?", hdr, re.M)}
+    A = pkg.lib
+    pairs = {"ALGO_AUTO": A.ALGO_AUTO, "ALGO_GEMV": A.ALGO_GEMV, "ALGO_FUSED_MMA": A.ALGO_FUSED_MMA, "ALGO_DEQUANT_MMA": A.ALGO_DEQUANT_MMA,
+             "ALGO_FUSED_TMEM": A.ALGO_FUSED_TMEM, "ALGO_GEMV_FAST": A.ALGO_GEMV_FAST, "ALGO_MASK": A.ALGO_MASK,
+             "FLAG_EXACT_W": A.FLAG_EXACT_W, "FLAG_GENERIC": A.FLAG_GENERIC, "FLAG_TILE384": A.FLAG_TILE384, "FLAG_NOSPLIT": A.FLAG_NOSPLIT,
+             "FLAG_UNSTAGED": A.FLAG_UNSTAGED, "FLAG_TILE192": A.FLAG_TILE192, "FLAG_W_STABLE": A.FLAG_W_STABLE,
+             "DEQUANT_SRC_STABLE": A.DEQUANT_SRC_STABLE, "F16": A.F16, "BF16": A.BF16, "F32": A.F32,
+             "OP_DEQUANT": A.OP_DEQUANT, "OP_LINEAR": A.OP_LINEAR, "OP_ROWS": A.OP_ROWS, "OP_LINEAR_MMA": A.OP_LINEAR_MMA}
+    for name, value in pairs.items():
+        assert defines.get(name) == value, (name, defines.get(name), value)
+    flags = [v for k, v in defines.items() if k.startswith("FLAG_")]
+    assert len(set(flags)) == len(flags) and all(f & A.ALGO_MASK == 0 and f & (f - 1) == 0 for f in flags), "flag bits must be distinct single bits above the algo mask"
+    assert defines["DEQUANT_SRC_STABLE"] > 2, "the stable-source bit must not collide with a dtype code"
